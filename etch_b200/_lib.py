@@ -1,0 +1,57 @@
+"""ctypes binding of libetch_b200.so (the C ABI declared in include/etch_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libetch_b200.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError("etch_b200: %s not found -- run `python -m etch_b200.build` (no CPU fallback exists)" % _SO)
+        _lib = ctypes.CDLL(_SO)
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("etch_b200: expected a CUDA tensor, got device %s" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("etch_b200: tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32(x):
+    return ctypes.c_float(float(x))
+
+
+def call(name, *args):
+    """Invoke ``int etch_<name>(..., cudaStream_t)`` on the current torch stream; raise on a non-zero status."""
+    fn = getattr(lib(), "etch_" + name)
+    fn.restype = ctypes.c_int
+    rc = fn(*args, stream())
+    if rc != 0:
+        raise RuntimeError("etch_b200: etch_%s failed with status %d (%s)" % (
+            name, rc, "invalid argument" if rc == -1 else "unsupported" if rc == -2 else "cudaError"))
+    return rc
+
+
+def exported_symbols():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _SO], capture_output=True, text=True).stdout
+    return sorted(l.split()[-1] for l in out.splitlines() if " T etch_" in l)

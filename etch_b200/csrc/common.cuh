@@ -1,0 +1,42 @@
+// Shared helpers for the etch_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define ETCH_OK 0
+#define ETCH_EINVAL (-1)       // bad argument (null pointer, size out of the supported range)
+#define ETCH_EUNSUPPORTED (-2) // reference entry point that is not on the hot path (stub)
+
+#define ETCH_API extern "C" __attribute__((visibility("default")))
+
+#define ETCH_RETURN_LAST()                         \
+    do {                                           \
+        cudaError_t e__ = cudaGetLastError();      \
+        return e__ == cudaSuccess ? ETCH_OK : (int)e__; \
+    } while (0)
+
+#define ETCH_TRY(x)                                 \
+    do {                                            \
+        cudaError_t e__ = (x);                      \
+        if (e__ != cudaSuccess) return (int)e__;    \
+    } while (0)
+
+// dx*dx + dy*dy + dz*dz exactly as nvcc contracts the reference expression (FMUL, FFMA, FFMA).
+__device__ __forceinline__ float etch_sqdist3(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ float etch_lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
+
+template <typename T>
+__host__ __device__ __forceinline__ T etch_cdiv(T a, T b) { return (a + b - 1) / b; }
+
+// Host: block size rule of the reference launchers (grouping_cuda_kernel.cu:29-33, pointops cuda_utils.h:10-13).
+static inline int etch_opt_n_threads(int work_size) {
+    const int pow_2 = (int)(log((double)work_size) / log(2.0));
+    int t = 1 << pow_2;
+    if (t > 1024) t = 1024;
+    if (t < 1) t = 1;
+    return t;
+}

@@ -1,0 +1,352 @@
+// Index kernels of the ETCH hot path: furthest point sampling (vgtk + pointops variants), ordered ball query,
+// channel-major gather, brute-force kNN.  All index-exact against the reference kernels, including tie rules:
+//   external/vgtk/vgtk/cuda/grouping_cuda_kernel.cu:67-113   ball_query_cuda_kernel
+//   external/vgtk/vgtk/cuda/grouping_cuda_kernel.cu:339-466  furthest_point_sampling_cuda_kernel (+ __update)
+//   external/vgtk/vgtk/cuda/gathering_cuda_kernel.cu:42-68   gather_points_forward_kernel
+//   external/pointops/src/knnquery/knnquery_cuda_kernel.cu:21-108
+//   external/pointops/src/sampling/sampling_cuda_kernel.cu:5-129
+//
+// B200 design notes
+//  * FPS is a chain of m-1 dependent arg-max steps, i.e. latency bound.  One CTA per scan keeps every point and its
+//    running min-distance in REGISTERS (x,y staged in shared memory for clouds > 10k points), reduces with
+//    redux.sync (2 REDUX per level) and needs ONE __syncthreads per step (double-buffered warp slots).  The
+//    reference needs 11 barriers + 2 global round trips of temp[] per step.
+//  * The reference arg-max winner among equal distances is decided by its strided scan (lowest k inside a thread)
+//    and its shared-memory tree (slot 0 vs slot s: lower slot wins on ties => the winner is the thread whose
+//    BIT-REVERSED id is smallest).  We reproduce that with a packed tie key instead of replaying the tree.
+//  * Ball query: one warp per query, ballot + popc ordered compaction, early exit.
+//  * kNN: one thread per query running the reference's max-heap verbatim (so equal-distance order is identical),
+//    supports staged through shared memory tiles.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ FPS
+// tie key: larger wins.  bits[30:21] = 1023 - bitrev_log2T(k mod T), bits[20:0] = 0x1FFFFF - k  (k < 2^21 - 1)
+__device__ __forceinline__ unsigned fps_tie_key(int k, int Tm1, int shift) {
+    const unsigned br = shift >= 32 ? 0u : (__brev((unsigned)(k & Tm1)) >> shift);
+    return ((1023u - br) << 21) | (0x1FFFFFu - (unsigned)k);
+}
+
+struct FpsSeg {
+    const float* xyz;  // BCN: channel-major base of this scan; PACKED: row-major base of the whole packed array
+    int n;             // points in this segment
+    int m;             // samples to draw
+    int base;          // PACKED: first row of the segment (indices are emitted as base + k)
+    int* out;          // where idx[0..m) of this segment go
+};
+
+template <bool PACKED>
+__device__ __forceinline__ void fps_load(const FpsSeg& s, int k, float& x, float& y, float& z) {
+    if (PACKED) {
+        const float* p = s.xyz + (size_t)(s.base + k) * 3;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    } else {
+        x = __ldg(s.xyz + k); y = __ldg(s.xyz + s.n + k); z = __ldg(s.xyz + 2 * (size_t)s.n + k);
+    }
+}
+
+// PPT points per thread.  SMEM_XY: x,y of every point live in shared memory, z and the running distance in
+// registers (for clouds that do not fit the 64-register budget of a 1024-thread CTA).
+template <int PPT, bool PACKED, bool SMEM_XY>
+__device__ __forceinline__ void fps_segment(const FpsSeg& s, int T_ref, float* sx, float* sy, uint2 (*slots)[32]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NT = blockDim.x, NW = NT >> 5;
+    const int Tm1 = T_ref - 1;
+    int lg = 0;
+    while ((1 << lg) < T_ref) ++lg;
+    const int shift = 32 - lg;
+
+    float px[SMEM_XY ? 1 : PPT], py[SMEM_XY ? 1 : PPT], pz[PPT], tmp[PPT];
+    unsigned valid = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int k = tid + i * NT;
+        float x = 0.f, y = 0.f, z = 0.f;
+        bool ok = k < s.n;
+        if (ok) {
+            fps_load<PACKED>(s, k, x, y, z);
+            if (!PACKED) {  // vgtk variant: points with |p|^2 <= 1e-3 never update temp and never win (:385-387)
+                const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+                if ((double)mag <= 1e-3) ok = false;
+            }
+        }
+        if constexpr (SMEM_XY) {
+            if (k < s.n) { sx[k] = x; sy[k] = y; }
+        } else {
+            px[i] = x; py[i] = y;
+        }
+        pz[i] = z;
+        tmp[i] = 1e10f;
+        if (ok) valid |= 1u << i;
+    }
+    if (tid == 0 && s.m > 0) s.out[0] = s.base;
+    for (int i = tid; i < 64; i += NT) slots[i >> 5][i & 31] = make_uint2(0u, 0u);
+    __syncthreads();
+
+    int old = 0;
+    for (int j = 1; j < s.m; ++j) {
+        float x1, y1, z1;
+        fps_load<PACKED>(s, old, x1, y1, z1);
+        unsigned bv = 0u, bt = 0u;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            if (valid & (1u << i)) {
+                const int k = tid + i * NT;
+                float x2, y2;
+                if constexpr (SMEM_XY) { x2 = sx[k]; y2 = sy[k]; } else { x2 = px[i]; y2 = py[i]; }
+                const float d = etch_sqdist3(x2 - x1, y2 - y1, pz[i] - z1);
+                const float d2 = fminf(d, tmp[i]);
+                tmp[i] = d2;
+                const unsigned vb = __float_as_uint(d2);  // d2 >= 0: bit pattern is monotone
+                const unsigned tk = fps_tie_key(k, Tm1, shift);
+                if (vb > bv || (vb == bv && tk > bt)) { bv = vb; bt = tk; }
+            }
+        }
+        const unsigned wv = __reduce_max_sync(0xffffffffu, bv);
+        const unsigned wt = __reduce_max_sync(0xffffffffu, bv == wv ? bt : 0u);
+        const int buf = j & 1;
+        if (lane == 0) slots[buf][warp] = make_uint2(wv, wt);
+        __syncthreads();
+        const uint2 sl = lane < NW ? slots[buf][lane] : make_uint2(0u, 0u);
+        const unsigned gv = __reduce_max_sync(0xffffffffu, sl.x);
+        const unsigned gt = __reduce_max_sync(0xffffffffu, sl.x == gv ? sl.y : 0u);
+        old = gt ? (int)(0x1FFFFFu - (gt & 0x1FFFFFu)) : 0;  // no candidate at all: reference keeps besti init
+        if (tid == 0) s.out[j] = s.base + old;
+    }
+}
+
+template <int PPT, bool SMEM_XY>
+__global__ void __launch_bounds__(1024, 1) fps_bcn_kernel(const float* __restrict__ xyz, int n, int m, int T_ref,
+                                                          int* __restrict__ idx) {
+    extern __shared__ float fps_smem[];
+    __shared__ uint2 slots[2][32];
+    FpsSeg s;
+    s.xyz = xyz + (size_t)blockIdx.x * 3 * n;
+    s.n = n; s.m = m; s.base = 0;
+    s.out = idx + (size_t)blockIdx.x * m;
+    fps_segment<PPT, false, SMEM_XY>(s, T_ref, fps_smem, fps_smem + n, slots);
+}
+
+template <int PPT, bool SMEM_XY>
+__global__ void __launch_bounds__(1024, 1) fps_packed_kernel(const float* __restrict__ xyz, const int* __restrict__ offset,
+                                                             const int* __restrict__ new_offset, int T_ref,
+                                                             int* __restrict__ idx) {
+    extern __shared__ float fps_smem[];
+    __shared__ uint2 slots[2][32];
+    const int b = blockIdx.x;
+    const int start_n = b == 0 ? 0 : offset[b - 1], end_n = offset[b];
+    const int start_m = b == 0 ? 0 : new_offset[b - 1], end_m = new_offset[b];
+    FpsSeg s;
+    s.xyz = xyz; s.n = end_n - start_n; s.m = end_m - start_m; s.base = start_n;
+    s.out = idx + start_m;
+    fps_segment<PPT, true, SMEM_XY>(s, T_ref, fps_smem, fps_smem + s.n, slots);
+}
+
+// ------------------------------------------------------------------------------------------------ ball query
+// one warp per query; idx [B,m,nsample] fully written (zero-fill semantics of grouping_cuda.cpp:80-82 included)
+__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz,
+                                                         int n, int m, float radius2, int nsample, int* __restrict__ idx) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= m) return;
+    const float* X = xyz + (size_t)b * 3 * n;
+    const float* Q = new_xyz + (size_t)b * 3 * m;
+    int* out = idx + ((size_t)b * m + j) * nsample;
+    const float qx = __ldg(Q + j), qy = __ldg(Q + m + j), qz = __ldg(Q + 2 * (size_t)m + j);
+    int cnt = 0;
+    for (int k0 = 0; k0 < n && cnt < nsample; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < n) {
+            const float d2 = etch_sqdist3(qx - __ldg(X + k), qy - __ldg(X + n + k), qz - __ldg(X + 2 * (size_t)n + k));
+            hit = d2 < radius2;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+        if (hit && pos < nsample) out[pos] = k;
+        cnt += __popc(mask);
+    }
+    if (cnt > nsample) cnt = nsample;
+    __syncwarp();
+    if (cnt < nsample) {
+        if (cnt > 0 && cnt < nsample - 1) {
+            // reference: idx[cnt+k] = idx[k] sequentially == periodic extension of the found prefix (:96-102)
+            for (int i = cnt + lane; i < nsample; i += 32) out[i] = out[i % cnt];
+        } else {
+            for (int i = cnt + lane; i < nsample; i += 32) out[i] = 0;  // cnt == nsample-1 (or 0): slot keeps zero init
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gather
+__global__ void gather_bcn_kernel(const float* __restrict__ points, const int* __restrict__ idx, int C, int n, int m,
+                                  float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)C * m) return;
+    const int c = (int)(t / m), j = (int)(t % m);
+    out[((size_t)b * C + c) * m + j] = __ldg(points + ((size_t)b * C + c) * n + __ldg(idx + (size_t)b * m + j));
+}
+
+// ------------------------------------------------------------------------------------------------ kNN
+template <int NS>
+__device__ __forceinline__ void knn_reheap(float* dist, int* idx, int k) {
+    int root = 0, child = 1;
+    while (child < k) {
+        if (child + 1 < k && dist[child + 1] > dist[child]) child++;
+        if (dist[root] > dist[child]) return;
+        const float tf = dist[root]; dist[root] = dist[child]; dist[child] = tf;
+        const int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
+        root = child;
+        child = root * 2 + 1;
+    }
+}
+
+constexpr int KNN_TILE = 512;
+
+// NS > 0: compile-time heap size; NS == 0: runtime nsample (<= 100, as the reference's best_dist[100])
+template <int NS>
+__global__ void __launch_bounds__(128) knn_packed_kernel(int m, int nsample_rt, const float* __restrict__ xyz,
+                                                         const float* __restrict__ new_xyz, const int* __restrict__ offset,
+                                                         const int* __restrict__ new_offset, int nbatch,
+                                                         int* __restrict__ idx, float* __restrict__ dist2) {
+    constexpr int CAP = NS > 0 ? NS : 100;
+    const int nsample = NS > 0 ? NS : nsample_rt;
+    __shared__ float tile[KNN_TILE * 3];
+    __shared__ int s_lo, s_hi;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = pt < m;
+    int start = 0, end = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        int bt = 0;
+        while (bt < nbatch - 1 && !(pt < __ldg(new_offset + bt))) bt++;
+        start = bt == 0 ? 0 : __ldg(offset + bt - 1);
+        end = __ldg(offset + bt);
+        qx = __ldg(new_xyz + (size_t)pt * 3); qy = __ldg(new_xyz + (size_t)pt * 3 + 1); qz = __ldg(new_xyz + (size_t)pt * 3 + 2);
+    }
+    if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = 0; }
+    __syncthreads();
+    if (active) { atomicMin(&s_lo, start); atomicMax(&s_hi, end); }
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi;
+
+    float best_dist[CAP];
+    int best_idx[CAP];
+    for (int i = 0; i < nsample; ++i) { best_dist[i] = 1e10f; best_idx[i] = start; }
+    float root = 1e10f;
+
+    for (int t0 = lo; t0 < hi; t0 += KNN_TILE) {
+        const int cntp = min(KNN_TILE, hi - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cntp * 3; i += blockDim.x) tile[i] = __ldg(xyz + (size_t)t0 * 3 + i);
+        __syncthreads();
+        if (active) {
+            const int a = max(start, t0) - t0, e = min(end, t0 + cntp) - t0;
+            for (int i = a; i < e; ++i) {
+                const float d2 = etch_sqdist3(qx - tile[i * 3], qy - tile[i * 3 + 1], qz - tile[i * 3 + 2]);
+                if (d2 < root) {
+                    best_dist[0] = d2;
+                    best_idx[0] = t0 + i;
+                    knn_reheap<NS>(best_dist, best_idx, nsample);
+                    root = best_dist[0];
+                }
+            }
+        }
+    }
+    if (!active) return;
+    for (int i = nsample - 1; i > 0; i--) {  // heap_sort (:39-48)
+        const float tf = best_dist[0]; best_dist[0] = best_dist[i]; best_dist[i] = tf;
+        const int ti = best_idx[0]; best_idx[0] = best_idx[i]; best_idx[i] = ti;
+        knn_reheap<NS>(best_dist, best_idx, i);
+    }
+    for (int i = 0; i < nsample; ++i) {
+        idx[(size_t)pt * nsample + i] = best_idx[i];
+        dist2[(size_t)pt * nsample + i] = best_dist[i];
+    }
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+// replaces epn_grouping.furthest_point_sampling (external/vgtk/vgtk/cuda/grouping_cuda.cpp:160-174)
+ETCH_API int etch_fps_bcn(const float* xyz, int B, int n, int m, int* idx, cudaStream_t stream) {
+    if (!xyz || !idx || B <= 0 || n <= 0 || m < 0 || n > 28672) return ETCH_EINVAL;
+    if (m == 0) return ETCH_OK;
+    const int T = etch_opt_n_threads(n);
+    const int nt = n >= 1024 ? 1024 : ((n + 31) / 32) * 32;
+    const int ppt = (n + nt - 1) / nt;
+#define L(P, SX)                                                                                               \
+    {                                                                                                          \
+        auto kern = fps_bcn_kernel<P, SX>;                                                                     \
+        const size_t sm = (SX) ? (size_t)n * 8 : 0;                                                            \
+        if (sm > 48 * 1024) ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        kern<<<B, nt, sm, stream>>>(xyz, n, m, T, idx);                                                        \
+    }
+    if (ppt <= 1) L(1, false) else if (ppt <= 2) L(2, false) else if (ppt <= 3) L(3, false) else if (ppt <= 4) L(4, false)
+    else if (ppt <= 5) L(5, false) else if (ppt <= 6) L(6, false) else if (ppt <= 8) L(8, false) else if (ppt <= 10) L(10, false)
+    else if (ppt <= 12) L(12, true) else if (ppt <= 16) L(16, true) else if (ppt <= 20) L(20, true) else if (ppt <= 24) L(24, true)
+    else L(28, true)
+#undef L
+    ETCH_RETURN_LAST();
+}
+
+// replaces pointops_cuda.furthestsampling_cuda (external/pointops/src/sampling/sampling_cuda.cpp:8-16).
+// `tmp` (the reference's 1e10-filled scratch) is accepted for signature parity and left untouched.
+ETCH_API int etch_fps_packed(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp,
+                             int* idx, cudaStream_t stream) {
+    (void)tmp;
+    if (!xyz || !offset || !new_offset || !idx || b <= 0 || n_max <= 0 || n_max > 28672) return ETCH_EINVAL;
+    const int T = etch_opt_n_threads(n_max);
+    const int nt = n_max >= 1024 ? 1024 : ((n_max + 31) / 32) * 32;
+    const int ppt = (n_max + nt - 1) / nt;
+#define L(P, SX)                                                                                               \
+    {                                                                                                          \
+        auto kern = fps_packed_kernel<P, SX>;                                                                  \
+        const size_t sm = (SX) ? (size_t)n_max * 8 : 0;                                                        \
+        if (sm > 48 * 1024) ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        kern<<<b, nt, sm, stream>>>(xyz, offset, new_offset, T, idx);                                          \
+    }
+    if (ppt <= 1) L(1, false) else if (ppt <= 2) L(2, false) else if (ppt <= 3) L(3, false) else if (ppt <= 4) L(4, false)
+    else if (ppt <= 5) L(5, false) else if (ppt <= 6) L(6, false) else if (ppt <= 8) L(8, false) else if (ppt <= 10) L(10, false)
+    else if (ppt <= 12) L(12, true) else if (ppt <= 16) L(16, true) else if (ppt <= 20) L(20, true) else if (ppt <= 24) L(24, true)
+    else L(28, true)
+#undef L
+    ETCH_RETURN_LAST();
+}
+
+// replaces epn_grouping.ball_query (grouping_cuda.cpp:71-86); idx [B,m,nsample] is fully written
+ETCH_API int etch_ball_query_bcn(const float* new_xyz, const float* xyz, int B, int m, int n, float radius, int nsample,
+                                 int* idx, cudaStream_t stream) {
+    if (!new_xyz || !xyz || !idx || B <= 0 || m <= 0 || n <= 0 || nsample <= 0) return ETCH_EINVAL;
+    const float radius2 = radius * radius;
+    dim3 grid(etch_cdiv(m, 8), B);
+    ball_query_kernel<<<grid, 256, 0, stream>>>(new_xyz, xyz, n, m, radius2, nsample, idx);
+    ETCH_RETURN_LAST();
+}
+
+// replaces epn_gathering.gather_points_forward (gathering_cuda.cpp:29-43)
+ETCH_API int etch_gather_bcn(const float* points, const int* idx, int B, int C, int n, int m, float* out,
+                             cudaStream_t stream) {
+    if (!points || !idx || !out || B <= 0 || C <= 0 || n <= 0 || m <= 0) return ETCH_EINVAL;
+    dim3 grid((unsigned)etch_cdiv((size_t)C * m, (size_t)256), B);
+    gather_bcn_kernel<<<grid, 256, 0, stream>>>(points, idx, C, n, m, out);
+    ETCH_RETURN_LAST();
+}
+
+// replaces pointops_cuda.knnquery_cuda (external/pointops/src/knnquery/knnquery_cuda.cpp:8-17); nbatch = len(offset)
+ETCH_API int etch_knn_packed(int m, int nsample, const float* xyz, const float* new_xyz, const int* offset,
+                             const int* new_offset, int nbatch, int* idx, float* dist2, cudaStream_t stream) {
+    if (!xyz || !new_xyz || !offset || !new_offset || !idx || !dist2 || m <= 0 || nsample <= 0 || nsample > 100 || nbatch <= 0)
+        return ETCH_EINVAL;
+    const int grid = etch_cdiv(m, 128);
+    if (nsample == 3) knn_packed_kernel<3><<<grid, 128, 0, stream>>>(m, 3, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else if (nsample == 8) knn_packed_kernel<8><<<grid, 128, 0, stream>>>(m, 8, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else if (nsample == 16) knn_packed_kernel<16><<<grid, 128, 0, stream>>>(m, 16, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else knn_packed_kernel<0><<<grid, 128, 0, stream>>>(m, nsample, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_opt_threads(int work_size) { return etch_opt_n_threads(work_size); }
