@@ -1,0 +1,472 @@
+// PointTransformer heads (magnitude net, marker-label/confidence net) -- packed-row kernels.
+//
+// Reference semantics restated:
+//   src/models/pointtransformer_seg.py:8-37     PointTransformerLayer (vector attention over kNN, share_planes 8)
+//   src/models/pointtransformer_seg.py:40-68    TransitionDown (FPS + kNN group + Linear + BN + ReLU + max-pool)
+//   src/models/pointtransformer_seg.py:71-98    TransitionUp  (head: per-scan mean; else 3-NN inverse-distance interpolation)
+//   src/models/pointtransformer_seg.py:101-122  PointTransformerBlock
+//   src/models/pointtransformer_seg.py:144-145,181-192  cls / confi heads, softmax-weighted confidence
+//   src/models/pointops.py:79-100,164-178       queryandgroup, interpolation (weights 1/(sqrt(d2)+1e-8))
+// All BatchNorm layers run in eval mode => folded on the host into per-channel scale/shift of the producing linear.
+//
+// B200 design: every Linear(+BN)(+ReLU)(+residual) is ONE generic fused GEMM launch; the per-neighbour
+// Linear(3+c -> c') of TransitionDown is split into a per-source-point GEMM + a 3-term geometric correction so it runs
+// once per point instead of once per (point, neighbour); the attention layer never materialises the
+// [n, nsample, c] tensors (k-q+p_r, v+p_r, weights) -- one warp owns a point and recomputes p_r in both passes; the
+// confidence head never materialises the [B, 11008, N] activation (220 MB/scan).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ generic fused linear
+// Y[n][co] = relu?( (X[n][ci] * Wt[ci][co] + seg[b(n)][co]) * scale[co] + shift[co] + R[n][co] )
+constexpr int LBM = 64, LBN = 64, LBK = 16;
+
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Wt,
+                                                     int n, int ci, int co, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, const float* __restrict__ R,
+                                                     const float* __restrict__ seg, const int* __restrict__ seg_off,
+                                                     int nseg, int relu, float* __restrict__ Y, int ldy) {
+    __shared__ __align__(16) float sA[LBK][LBM + 4];
+    __shared__ __align__(16) float sB[LBK][LBN];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * LBM, n0 = blockIdx.y * LBN;
+    const int tr = tid & 15, tc = tid >> 4;  // rows 4tr.., cols 4tc..
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < ci; k0 += LBK) {
+        __syncthreads();
+        for (int i = tid; i < LBM * LBK; i += 256) {
+            const int r = i / LBK, k = i % LBK;
+            const int gm = m0 + r, gk = k0 + k;
+            sA[k][r] = (gm < n && gk < ci) ? __ldg(X + (size_t)gm * ldx + gk) : 0.f;
+        }
+        for (int i = tid; i < LBK * LBN; i += 256) {
+            const int k = i / LBN, c = i % LBN;
+            const int gk = k0 + k, gc = n0 + c;
+            sB[k][c] = (gk < ci && gc < co) ? __ldg(Wt + (size_t)gk * co + gc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < LBK; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&sA[k][tr * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&sB[k][tc * 4]);
+            const float a[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + tr * 4 + i;
+        if (gm >= n) continue;
+        int sb = 0;
+        if (seg) { while (sb < nseg - 1 && gm >= __ldg(seg_off + sb)) ++sb; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gc = n0 + tc * 4 + j;
+            if (gc >= co) continue;
+            float v = acc[i][j];
+            if (seg) v += __ldg(seg + (size_t)sb * co + gc);
+            if (scale) v *= __ldg(scale + gc);
+            if (shift) v += __ldg(shift + gc);
+            if (R) v += __ldg(R + (size_t)gm * co + gc);
+            if (relu) v = fmaxf(v, 0.f);
+            Y[(size_t)gm * ldy + gc] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ vector attention
+struct AttnW {
+    const float* P0;   // [3][3] Linear(3,3) with BN(3) folded: pr3 = relu(P0 d + p0b)
+    const float* p0b;  // [3]
+    const float* P3;   // [c][3]
+    const float* p3b;  // [c]
+    const float* s0;   // [c]  BN(c) scale on (k - q + p_r)
+    const float* h0;   // [c]  shift
+    const float* W1;   // [T][c]  Linear(c, c/8) with BN(c/8) folded
+    const float* b1;   // [T]
+    const float* W2;   // [T][T]
+    const float* b2;   // [T]
+    const float* so;   // [c]  bn2 of the enclosing block, folded scale
+    const float* ho;   // [c]  shift
+};
+
+template <int R>  // R = c / 32
+__global__ void __launch_bounds__(256) pt_attn_kernel(const float* __restrict__ p, const float* __restrict__ qkv,
+                                                      const int* __restrict__ idx, AttnW W, int n, int ns,
+                                                      float* __restrict__ out) {
+    constexpr int C = R * 32, T = C / 8, TL = (T + 31) / 32;
+    extern __shared__ __align__(16) float sm[];
+    float* s_W1 = sm;                 // [T][C]
+    float* s_log = sm + T * C;        // [8 warps][16][T]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < T * C; i += 256) s_W1[i] = __ldg(W.W1 + i);
+    __syncthreads();
+    float P0[9], p0b[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P0[i] = __ldg(W.P0 + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p0b[i] = __ldg(W.p0b + i);
+    float P3[R][3], p3b[R], s0[R], h0[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int ch = lane + 32 * r;
+        P3[r][0] = __ldg(W.P3 + ch * 3); P3[r][1] = __ldg(W.P3 + ch * 3 + 1); P3[r][2] = __ldg(W.P3 + ch * 3 + 2);
+        p3b[r] = __ldg(W.p3b + ch); s0[r] = __ldg(W.s0 + ch); h0[r] = __ldg(W.h0 + ch);
+    }
+    float* lg = s_log + warp * 16 * T;
+    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+        const float pix = __ldg(p + (size_t)i * 3), piy = __ldg(p + (size_t)i * 3 + 1), piz = __ldg(p + (size_t)i * 3 + 2);
+        float qv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) qv[r] = __ldg(qkv + (size_t)i * 3 * C + lane + 32 * r);
+        // ---- pass 1: attention logits per (neighbour, shared plane) ----
+        for (int j = 0; j < ns; ++j) {
+            const int nb = __ldg(idx + (size_t)i * ns + j);
+            const float dx = __ldg(p + (size_t)nb * 3) - pix, dy = __ldg(p + (size_t)nb * 3 + 1) - piy,
+                        dz = __ldg(p + (size_t)nb * 3 + 2) - piz;
+            float e[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) e[a] = fmaxf(fmaf(P0[a * 3 + 2], dz, fmaf(P0[a * 3 + 1], dy, fmaf(P0[a * 3], dx, p0b[a]))), 0.f);
+            float wp[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float pr = fmaf(P3[r][2], e[2], fmaf(P3[r][1], e[1], fmaf(P3[r][0], e[0], p3b[r])));
+                const float kv = __ldg(qkv + (size_t)nb * 3 * C + C + lane + 32 * r);
+                wp[r] = fmaxf(fmaf(kv - qv[r] + pr, s0[r], h0[r]), 0.f);
+            }
+            float hh[TL];
+#pragma unroll
+            for (int u = 0; u < TL; ++u) hh[u] = 0.f;
+            for (int t = 0; t < T; ++t) {
+                float part = 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) part = fmaf(s_W1[t * C + lane + 32 * r], wp[r], part);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if ((t & 31) == lane) hh[t >> 5] = fmaxf(part + __ldg(W.b1 + t), 0.f);
+            }
+            // second small linear T -> T (each lane owns outputs t' = lane, lane+32)
+            float o2[TL];
+#pragma unroll
+            for (int u = 0; u < TL; ++u) o2[u] = (lane + 32 * u < T) ? __ldg(W.b2 + lane + 32 * u) : 0.f;
+            for (int t = 0; t < T; ++t) {
+                const float hv = __shfl_sync(0xffffffffu, hh[t >> 5], t & 31);
+#pragma unroll
+                for (int u = 0; u < TL; ++u)
+                    if (lane + 32 * u < T) o2[u] = fmaf(__ldg(W.W2 + (lane + 32 * u) * T + t), hv, o2[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < TL; ++u)
+                if (lane + 32 * u < T) lg[j * T + lane + 32 * u] = o2[u];
+        }
+        __syncwarp();
+        // ---- softmax over the neighbours, per shared plane ----
+#pragma unroll
+        for (int u = 0; u < TL; ++u) {
+            const int t = lane + 32 * u;
+            if (t < T) {
+                float mx = -INFINITY;
+                for (int j = 0; j < ns; ++j) mx = fmaxf(mx, lg[j * T + t]);
+                float s = 0.f;
+                for (int j = 0; j < ns; ++j) { const float ev = expf(lg[j * T + t] - mx); lg[j * T + t] = ev; s += ev; }
+                const float inv = 1.0f / s;
+                for (int j = 0; j < ns; ++j) lg[j * T + t] *= inv;
+            }
+        }
+        __syncwarp();
+        // ---- pass 2: aggregate (v + p_r) with the shared-plane weights ----
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        for (int j = 0; j < ns; ++j) {
+            const int nb = __ldg(idx + (size_t)i * ns + j);
+            const float dx = __ldg(p + (size_t)nb * 3) - pix, dy = __ldg(p + (size_t)nb * 3 + 1) - piy,
+                        dz = __ldg(p + (size_t)nb * 3 + 2) - piz;
+            float e[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) e[a] = fmaxf(fmaf(P0[a * 3 + 2], dz, fmaf(P0[a * 3 + 1], dy, fmaf(P0[a * 3], dx, p0b[a]))), 0.f);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int ch = lane + 32 * r;
+                const float pr = fmaf(P3[r][2], e[2], fmaf(P3[r][1], e[1], fmaf(P3[r][0], e[0], p3b[r])));
+                const float vv = __ldg(qkv + (size_t)nb * 3 * C + 2 * C + ch);
+                acc[r] = fmaf(vv + pr, lg[j * T + (ch % T)], acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int ch = lane + 32 * r;
+            out[(size_t)i * C + ch] = fmaxf(fmaf(acc[r], __ldg(W.so + ch), __ldg(W.ho + ch)), 0.f);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ transition down
+// out[i][co] = max_j relu( (Wp[co] . (p[nb_j] - np[i]) + Yx[nb_j][co]) * scale[co] + shift[co] )
+__global__ void __launch_bounds__(256) pt_down_pool_kernel(const float* __restrict__ p, const float* __restrict__ np_,
+                                                           const float* __restrict__ Yx, const int* __restrict__ idx,
+                                                           const float* __restrict__ Wp, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, int m, int ns, int co,
+                                                           float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= m) return;
+    const float cx = __ldg(np_ + (size_t)i * 3), cy = __ldg(np_ + (size_t)i * 3 + 1), cz = __ldg(np_ + (size_t)i * 3 + 2);
+    for (int c = lane; c < co; c += 32) {
+        const float w0 = __ldg(Wp + c * 3), w1 = __ldg(Wp + c * 3 + 1), w2 = __ldg(Wp + c * 3 + 2);
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        float best = -INFINITY;
+        for (int j = 0; j < ns; ++j) {
+            const int nb = __ldg(idx + (size_t)i * ns + j);
+            const float dx = __ldg(p + (size_t)nb * 3) - cx, dy = __ldg(p + (size_t)nb * 3 + 1) - cy, dz = __ldg(p + (size_t)nb * 3 + 2) - cz;
+            const float lin = fmaf(w2, dz, fmaf(w1, dy, fmaf(w0, dx, __ldg(Yx + (size_t)nb * co + c))));
+            best = fmaxf(best, fmaxf(fmaf(lin, sc, sh), 0.f));
+        }
+        out[(size_t)i * co + c] = best;
+    }
+}
+
+// out[i][c] = a[i][c] + sum_k w_k f[idx_k][c],  w_k = (1/(sqrt(d2_k)+1e-8)) / sum   (pointops.interpolation)
+__global__ void __launch_bounds__(256) pt_interp_add_kernel(const float* __restrict__ a, const float* __restrict__ f,
+                                                            const int* __restrict__ idx, const float* __restrict__ d2,
+                                                            int n, int c, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float w[3];
+    int id[3];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        id[k] = __ldg(idx + (size_t)i * 3 + k);
+        w[k] = 1.0f / (sqrtf(__ldg(d2 + (size_t)i * 3 + k)) + 1e-8f);
+        s += w[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] /= s;
+    for (int ch = lane; ch < c; ch += 32) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v += __ldg(f + (size_t)id[k] * c + ch) * w[k];
+        out[(size_t)i * c + ch] = __ldg(a + (size_t)i * c + ch) + v;
+    }
+}
+
+// per-segment mean of packed rows: out[b][c] = mean_{rows of segment b} x[row][c]
+__global__ void __launch_bounds__(256) seg_mean_kernel(const float* __restrict__ x, const int* __restrict__ off, int c,
+                                                       float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int s = b == 0 ? 0 : __ldg(off + b - 1), e = __ldg(off + b);
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float acc = 0.f;
+        for (int r = s; r < e; ++r) acc += __ldg(x + (size_t)r * c + ch);
+        out[(size_t)b * c + ch] = acc / (float)(e - s);
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx, int m, int c,
+                                   float* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)m * c) return;
+    const int i = (int)(t / c), ch = (int)(t % c);
+    out[t] = __ldg(x + (size_t)__ldg(idx + i) * c + ch);
+}
+
+// ------------------------------------------------------------------------------------------------ confidence head
+// conf[m] = sum_l softmax(logits[m])_l * ( b2[l] + sum_u w2[l][u] * relu(b0[l*128+u] + sum_k x[m][k] W0t[k][l*128+u]) )
+constexpr int CH_M = 64;
+__global__ void __launch_bounds__(256, 1) conf_head_kernel(const float* __restrict__ x,       // [n][128]
+                                                           const float* __restrict__ logits,  // [n][K]
+                                                           const float* __restrict__ W0t,     // [128][K*128]
+                                                           const float* __restrict__ b0,      // [K*128]
+                                                           const float* __restrict__ w2,      // [K][128]
+                                                           const float* __restrict__ b2,      // [K]
+                                                           int n, int K, float* __restrict__ conf) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_x = sm;                      // [128 k][CH_M + 4]
+    float* s_w = s_x + 128 * (CH_M + 4);  // [128 k][128 u]
+    float* s_p = s_w + 128 * 128;         // [CH_M][K] softmax
+    float* s_c = s_p + CH_M * K;          // [CH_M]
+    const int tid = threadIdx.x, tc = tid & 15, tr = tid >> 4;
+    constexpr int LDX = CH_M + 4;
+    for (int tile = blockIdx.x; tile * CH_M < n; tile += gridDim.x) {
+        const int m0 = tile * CH_M;
+        __syncthreads();
+        for (int i = tid; i < CH_M * 128; i += 256) {
+            const int r = i >> 7, k = i & 127;
+            s_x[k * LDX + r] = (m0 + r < n) ? __ldg(x + (size_t)(m0 + r) * 128 + k) : 0.f;
+        }
+        if (tid < CH_M) {
+            s_c[tid] = 0.f;
+            if (m0 + tid < n) {
+                const float* lr = logits + (size_t)(m0 + tid) * K;
+                float mx = -INFINITY;
+                for (int l = 0; l < K; ++l) mx = fmaxf(mx, __ldg(lr + l));
+                float s = 0.f;
+                for (int l = 0; l < K; ++l) { const float e = expf(__ldg(lr + l) - mx); s_p[tid * K + l] = e; s += e; }
+                const float inv = 1.0f / s;
+                for (int l = 0; l < K; ++l) s_p[tid * K + l] *= inv;
+            } else {
+                for (int l = 0; l < K; ++l) s_p[tid * K + l] = 0.f;
+            }
+        }
+        for (int l = 0; l < K; ++l) {
+            __syncthreads();
+            for (int i = tid; i < 128 * 32; i += 256) {
+                const int k = i >> 5, c4 = i & 31;
+                reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(W0t + (size_t)k * K * 128 + (size_t)l * 128) + c4);
+            }
+            __syncthreads();
+            float acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < 128; ++k) {
+                const float4 av = *reinterpret_cast<const float4*>(s_x + k * LDX + tr * 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * 128 + tc * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + k * 128 + tc * 8 + 4);
+                const float a[4] = {av.x, av.y, av.z, av.w};
+                const float bb[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int u = tc * 8 + j;
+                const float bb = __ldg(b0 + (size_t)l * 128 + u), ww = __ldg(w2 + (size_t)l * 128 + u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[i] = fmaf(fmaxf(acc[i][j] + bb, 0.f), ww, part[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
+            }
+            if (tc == 0) {
+                const float bl = __ldg(b2 + l);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = tr * 4 + i;
+                    s_c[r] = fmaf(s_p[r * K + l], part[i] + bl, s_c[r]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < CH_M && m0 + tid < n) conf[m0 + tid] = s_c[tid];
+    }
+}
+
+// labels = argmax logits (first maximum), vec = dir*mag/scale, inner = p - vec   (eval.py:103,116,183)
+__global__ void postprocess_kernel(const float* __restrict__ p, const float* __restrict__ logits, const float* __restrict__ dir,
+                                   const float* __restrict__ mag, int n, int K, float inv_scale, long long* __restrict__ labels,
+                                   float* __restrict__ vec, float* __restrict__ inner) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* lr = logits + (size_t)i * K;
+    float best = __ldg(lr);
+    int bi = 0;
+    for (int l = 1; l < K; ++l) { const float v = __ldg(lr + l); if (v > best) { best = v; bi = l; } }
+    labels[i] = bi;
+    const float mg = __ldg(mag + i);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float v = __ldg(dir + (size_t)i * 3 + a) * mg * inv_scale;
+        vec[(size_t)i * 3 + a] = v;
+        inner[(size_t)i * 3 + a] = __ldg(p + (size_t)i * 3 + a) - v;
+    }
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+// Y = relu?((X Wt + seg[row's segment]) * scale + shift + R).  Any of scale/shift/R/seg may be NULL.
+// Replaces nn.Linear / nn.Conv1d(k=1) (+ eval BatchNorm1d + ReLU + residual) of pointtransformer_seg.py.
+ETCH_API int etch_linear(const float* X, int ldx, const float* Wt, int n, int ci, int co, const float* scale,
+                         const float* shift, const float* R, const float* seg, const int* seg_off, int nseg, int relu,
+                         float* Y, int ldy, cudaStream_t stream) {
+    if (!X || !Wt || !Y || n <= 0 || ci <= 0 || co <= 0) return ETCH_EINVAL;
+    dim3 grid(etch_cdiv(n, LBM), etch_cdiv(co, LBN));
+    linear_kernel<<<grid, 256, 0, stream>>>(X, ldx, Wt, n, ci, co, scale, shift, R, seg, seg_off, nseg, relu, Y, ldy);
+    ETCH_RETURN_LAST();
+}
+
+// PointTransformerLayer core + bn2 + ReLU of the enclosing block. qkv = [n][3c] (q | k | v), idx = self kNN [n][ns].
+ETCH_API int etch_pt_attention(const float* p, const float* qkv, const int* idx, const float* P0, const float* p0b,
+                               const float* P3, const float* p3b, const float* s0, const float* h0, const float* W1,
+                               const float* b1, const float* W2, const float* b2, const float* so, const float* ho, int n,
+                               int ns, int c, float* out, cudaStream_t stream) {
+    if (!p || !qkv || !idx || !out || n <= 0 || ns <= 0 || ns > 16) return ETCH_EINVAL;
+    AttnW W{P0, p0b, P3, p3b, s0, h0, W1, b1, W2, b2, so, ho};
+    const int T = c / 8;
+    const size_t smem = ((size_t)T * c + (size_t)8 * 16 * T) * 4;
+    int grid = etch_cdiv(n, 8);
+    if (grid > 148 * 8) grid = 148 * 8;
+#define ATT(R)                                                                                                   \
+    {                                                                                                            \
+        auto kern = pt_attn_kernel<R>;                                                                           \
+        ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, 256, smem, stream>>>(p, qkv, idx, W, n, ns, out);                                           \
+    }
+    if (c == 64) ATT(2) else if (c == 128) ATT(4) else if (c == 256) ATT(8) else if (c == 512) ATT(16) else return ETCH_EINVAL;
+#undef ATT
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_pt_down_pool(const float* p, const float* new_p, const float* Yx, const int* idx, const float* Wp,
+                               const float* scale, const float* shift, int m, int ns, int co, float* out,
+                               cudaStream_t stream) {
+    if (!p || !new_p || !Yx || !idx || !Wp || !scale || !shift || !out || m <= 0) return ETCH_EINVAL;
+    pt_down_pool_kernel<<<etch_cdiv(m, 8), 256, 0, stream>>>(p, new_p, Yx, idx, Wp, scale, shift, m, ns, co, out);
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_pt_interp_add(const float* a, const float* f, const int* idx, const float* d2, int n, int c, float* out,
+                                cudaStream_t stream) {
+    if (!a || !f || !idx || !d2 || !out || n <= 0) return ETCH_EINVAL;
+    pt_interp_add_kernel<<<etch_cdiv(n, 8), 256, 0, stream>>>(a, f, idx, d2, n, c, out);
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_seg_mean(const float* x, const int* off, int nseg, int c, float* out, cudaStream_t stream) {
+    if (!x || !off || !out || nseg <= 0) return ETCH_EINVAL;
+    seg_mean_kernel<<<nseg, 256, 0, stream>>>(x, off, c, out);
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_gather_rows(const float* x, const int* idx, int m, int c, float* out, cudaStream_t stream) {
+    if (!x || !idx || !out || m <= 0) return ETCH_EINVAL;
+    gather_rows_kernel<<<(unsigned)etch_cdiv((size_t)m * c, (size_t)256), 256, 0, stream>>>(x, idx, m, c, out);
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_conf_head(const float* x, const float* logits, const float* W0t, const float* b0, const float* w2,
+                            const float* b2, int n, int K, float* conf, cudaStream_t stream) {
+    if (!x || !logits || !W0t || !b0 || !w2 || !b2 || !conf || n <= 0 || K <= 0 || K > 128) return ETCH_EINVAL;
+    const size_t smem = ((size_t)128 * (CH_M + 4) + 128 * 128 + (size_t)CH_M * K + CH_M) * 4;
+    ETCH_TRY(cudaFuncSetAttribute(conf_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = etch_cdiv(n, CH_M);
+    if (grid > 148 * 2) grid = 148 * 2;
+    conf_head_kernel<<<grid, 256, smem, stream>>>(x, logits, W0t, b0, w2, b2, n, K, conf);
+    ETCH_RETURN_LAST();
+}
+
+ETCH_API int etch_postprocess(const float* p, const float* logits, const float* dir, const float* mag, int n, int K,
+                              float scale_magnitude, long long* labels, float* vec, float* inner, cudaStream_t stream) {
+    if (!p || !logits || !dir || !mag || !labels || !vec || !inner || n <= 0) return ETCH_EINVAL;
+    postprocess_kernel<<<etch_cdiv(n, 256), 256, 0, stream>>>(p, logits, dir, mag, n, K, 1.0f / scale_magnitude, labels, vec, inner);
+    ETCH_RETURN_LAST();
+}

@@ -1,0 +1,97 @@
+"""Host-side driver of the SO(3)-equivariant encoder (EquivBackbone, src/models/so3net.py:11-33).
+
+Only orchestration lives here: weight re-layout at load time, buffer allocation, kernel launches through the C ABI.
+Feature tensors are point-major ``[B, P, 60, C]`` (the reference keeps ``[B, C, P, 60]``); use ``to_reference_layout``
+when comparing.
+"""
+import torch
+
+from .. import _lib as L
+from . import spec
+
+
+def to_reference_layout(feats_bpac):
+    """[B,P,60,C] -> the reference's [B,C,P,60]."""
+    return feats_bpac.permute(0, 3, 1, 2).contiguous()
+
+
+class EncoderPlan:
+    """Device-resident, kernel-friendly copies of the encoder weights (built once per state_dict/device)."""
+
+    def __init__(self, sd, device, input_radius=0.4, n_layers=2):
+        self.layers = []
+        self.device = device
+        f32 = dict(dtype=torch.float32, device=device)
+        for lp in spec.epn_layers(input_radius, n_layers):
+            pre = "encoder.backbone.%d.blocks.%d." % (lp["block"], lp["conv"])
+            ci, co = lp["dim_in"], lp["dim_out"]
+            anchors = sd[pre + "inter_conv.conv.anchors"].to(**f32)
+            kernels = sd[pre + "inter_conv.conv.kernels"].to(**f32)
+            # rotated kernel points R_a k  (functional.py:296): [60,24,3]
+            kr = torch.matmul(anchors, kernels.t()).permute(0, 2, 1).contiguous()
+            sigma = float(lp["sigma"])
+            krs = torch.cat([kr * (2.0 / sigma), (kr * kr).sum(-1, keepdim=True) / sigma], -1).contiguous()
+            W = sd[pre + "inter_conv.conv.basic_conv.W"].to(**f32)
+            Wi = sd[pre + "intra_conv.conv.basic_conv.W"].to(**f32)
+            d = dict(lp)
+            d.update(
+                kr=kr, krs=krs,
+                Wt_inter=W.t().contiguous(),  # [(c,k)][o]
+                b_inter=sd[pre + "inter_conv.conv.basic_conv.bias"].to(**f32).reshape(-1).contiguous(),
+                Wt_intra=Wi.view(co, co, 12).permute(2, 1, 0).contiguous(),  # [j][c][o]
+                b_intra=sd[pre + "intra_conv.conv.basic_conv.bias"].to(**f32).reshape(-1).contiguous(),
+                intra_idx=sd[pre + "intra_conv.conv.intra_idx"].to(device=device, dtype=torch.int32).contiguous(),
+                Wt_skip=sd[pre + "skip_conv.weight"].to(**f32).view(co, ci).t().contiguous(),  # [c][o]
+                b_skip=sd[pre + "skip_conv.bias"].to(**f32).contiguous(),
+            )
+            self.layers.append(d)
+        self.anchors = sd["encoder.backbone.0.blocks.0.inter_conv.conv.anchors"].to(**f32).contiguous()
+        self.ident = torch.arange(60, dtype=torch.int32, device=device)
+
+
+def run_encoder(plan, xyz_bcn, trace=None):
+    """xyz_bcn [B,3,N] f32 cuda -> (xyz [B,3,P2], feats [B,P2,60,64]).  Mirrors BasicSO3ConvBlock/SeparableSO3ConvBlock
+    (src/models/so3conv.py:125-183): inter conv -> IN+lrelu -> intra conv -> IN+lrelu, plus the skip branch."""
+    dev = xyz_bcn.device
+    B = xyz_bcn.shape[0]
+    xyz = xyz_bcn.contiguous()
+    feats = None
+    for lp in plan.layers:
+        q = xyz.shape[2]
+        ci, co, nn_ = lp["dim_in"], lp["dim_out"], lp["n_neighbor"]
+        P = -(-q // lp["stride"])
+        if q == P or lp["lazy_sample"]:  # pc/sample.py:75-79
+            sidx = torch.arange(P, dtype=torch.int32, device=dev).view(1, -1).expand(B, -1).contiguous()
+        else:
+            sidx = torch.empty(B, P, dtype=torch.int32, device=dev)
+            L.call("fps_bcn", L.ptr(xyz), B, q, P, L.ptr(sidx))
+        new_xyz = torch.empty(B, 3, P, dtype=torch.float32, device=dev)
+        L.call("gather_bcn", L.ptr(xyz), L.ptr(sidx), B, 3, q, P, L.ptr(new_xyz))
+        nbr = torch.empty(B, P, nn_, dtype=torch.int32, device=dev)
+        L.call("ball_query_bcn", L.ptr(new_xyz), L.ptr(xyz), B, P, q, L.f32(lp["radius"]), nn_, L.ptr(nbr))
+        stats = torch.zeros(3, B, co, 2, dtype=torch.float64, device=dev)
+        z1 = torch.empty(B, P, 60, co, dtype=torch.float32, device=dev)
+        if ci == 1:
+            L.call("so3_inter_conv_c1", L.ptr(xyz), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["kr"]), L.ptr(lp["Wt_inter"]),
+                   L.ptr(lp["b_inter"]), B, q, P, nn_, co, L.f32(lp["sigma"]), L.ptr(z1), L.ptr(stats[0]))
+        else:
+            L.call("so3_inter_conv", L.ptr(xyz), L.ptr(feats), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["krs"]),
+                   L.ptr(lp["Wt_inter"]), L.ptr(lp["b_inter"]), B, q, P, nn_, ci, co, L.f32(lp["sigma"]), L.ptr(z1),
+                   L.ptr(stats[0]))
+        z2 = torch.empty_like(z1)
+        L.call("so3_intra_conv", L.ptr(z1), L.ptr(stats[0]), L.ptr(lp["intra_idx"]), L.ptr(lp["Wt_intra"]),
+               L.ptr(lp["b_intra"]), B, P, co, co, L.ptr(z2), L.ptr(stats[1]))
+        out = torch.empty_like(z1)
+        if ci == 1:
+            # skip input is the constant occupancy feature: Conv1x1 gives a per-channel constant, whose InstanceNorm is 0
+            z3 = None
+            L.call("so3_combine", L.ptr(z2), L.ptr(stats[1]), L.ptr(None), L.ptr(None), B, P, co, L.ptr(out))
+        else:
+            z3 = torch.empty_like(z1)
+            L.call("so3_skip_conv", L.ptr(feats), L.ptr(sidx), L.ptr(plan.ident), L.ptr(lp["Wt_skip"]), L.ptr(lp["b_skip"]),
+                   B, q, P, ci, co, L.ptr(z3), L.ptr(stats[2]))
+            L.call("so3_combine", L.ptr(z2), L.ptr(stats[1]), L.ptr(z3), L.ptr(stats[2]), B, P, co, L.ptr(out))
+        if trace is not None:
+            trace.append(dict(sample_idx=sidx, ball_idx=nbr, xyz=new_xyz, inter_z=z1, intra_z=z2, skip_z=z3, out=out))
+        xyz, feats = new_xyz, out
+    return xyz, feats
