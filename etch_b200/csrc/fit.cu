@@ -1,0 +1,578 @@
+// SMPL marker fit: marker extraction, two-stage Levenberg-Marquardt with an ANALYTIC marker-only Jacobian, full-mesh LBS.
+//
+// Reference semantics restated:
+//   src/models/fit_SMPL.py:17-62      get_markers (per label: top-3 confidences, weights conf^20, weighted centroid)
+//   src/models/fit_SMPL.py:111-152    marker residual  r = mask * (pred_marker - V[marker_vid])
+//   src/models/fit_SMPL.py:157-255    2 x theseus LevenbergMarquardt (30 its step .5 damping .01; 50 its step .2 damping 1e-3)
+//   external/smplx/smplx/lbs.py:153-398  lbs / blend_shapes / vertices2joints / batch_rodrigues (+1e-8) / batch_rigid_transform
+//   external/smplx/smplx/body_models.py:386-414, vertex_joint_selector.py:29-80   joints = 24 chain + 21 picked vertices
+//
+// B200 design: the reference differentiates 258 residuals through a full 6890-vertex LBS with autograd (~2 GFLOP per
+// iteration and hundreds of launches).  Only 86 vertices matter, so one persistent CTA per scan keeps the whole solve in
+// shared memory: forward kinematics, the 86 marker vertices, the closed-form Jacobian (258 x 85), J^T J + lambda I, a
+// dense Cholesky and the update -- 80 iterations without leaving the SM; marker rows of the blend-shape bases are the
+// only global reads (L2-resident, shared by all scans).  The full mesh is skinned once at the end.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NJ = 24;
+constexpr int NM_MAX = 96;     // markers supported by the shared-memory layout
+constexpr int DMAX = 85;       // 72 pose + 10 betas + 3 transl
+constexpr int LDJ = 88;        // padded leading dimension of J
+constexpr int LDA = 89;        // padded leading dimension of A = J^T J
+
+// ------------------------------------------------------------------------------------------------ markers
+// one warp per (scan, label): top-3 confidences among the points carrying that label (ties: lower point index first)
+__global__ void __launch_bounds__(256) markers_kernel(const float* __restrict__ inner, const long long* __restrict__ labels,
+                                                      const float* __restrict__ conf, int N, int M,
+                                                      float* __restrict__ markers, unsigned char* __restrict__ valid) {
+    const int b = blockIdx.y;
+    const int label = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (label >= M) return;
+    float c[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int id[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+    int cnt = 0;
+    const long long* L = labels + (size_t)b * N;
+    const float* C = conf + (size_t)b * N;
+    for (int i = lane; i < N; i += 32) {
+        if (L[i] == label) {
+            ++cnt;
+            const float v = C[i];
+            // insert (v, i): larger v first, then smaller i
+            if (v > c[2] || (v == c[2] && i < id[2])) {
+                c[2] = v; id[2] = i;
+                if (c[2] > c[1] || (c[2] == c[1] && id[2] < id[1])) { float t = c[1]; c[1] = c[2]; c[2] = t; int u = id[1]; id[1] = id[2]; id[2] = u; }
+                if (c[1] > c[0] || (c[1] == c[0] && id[1] < id[0])) { float t = c[0]; c[0] = c[1]; c[1] = t; int u = id[0]; id[0] = id[1]; id[1] = u; }
+            }
+        }
+    }
+    // merge the 32 sorted triples: three rounds of warp arg-max extraction
+    int total = cnt;
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    float tc[3]; int ti[3];
+    int head = 0;
+    for (int r = 0; r < 3; ++r) {
+        float v = head < 3 ? c[head] : -INFINITY;
+        int iv = head < 3 ? id[head] : 0x7fffffff;
+        float bv = v; int bi = iv;
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        tc[r] = bv; ti[r] = bi;
+        if (head < 3 && iv == bi && bi != 0x7fffffff) ++head;
+    }
+    if (lane == 0) {
+        float* out = markers + ((size_t)b * M + label) * 3;
+        if (total == 0) {
+            out[0] = out[1] = out[2] = 0.f;
+            valid[(size_t)b * M + label] = 0;
+        } else {
+            const int k = total < 3 ? total : 3;
+            float ws = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int r = 0; r < k; ++r) {
+                const float w = powf(tc[r], 20.0f);
+                const float* p = inner + ((size_t)b * N + ti[r]) * 3;
+                sx += p[0] * w; sy += p[1] * w; sz += p[2] * w; ws += w;
+            }
+            out[0] = sx / ws; out[1] = sy / ws; out[2] = sz / ws;
+            valid[(size_t)b * M + label] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ body constants
+struct BodyMarkers {           // marker-restricted SMPL tables (device pointers)
+    const float* Tm;           // [M][3]      v_template[vid]
+    const float* Sm;           // [M][3][10]  shapedirs[vid]
+    const float* Pm;           // [207][M*3]  posedirs[:, vid*3+c]
+    const float* Wm;           // [M][24]     lbs_weights[vid]
+    const float* Jt;           // [24][3]     J_regressor v_template
+    const float* Js;           // [24][3][10] J_regressor shapedirs
+    const int* parents;        // [24]
+    const unsigned* ancmask;   // [24]  bit j set iff joint j is an ancestor-or-self of the joint
+    int M;
+};
+
+// Rodrigues exactly as lbs.batch_rodrigues (:295-330): angle = |r + 1e-8|, K = [r/angle]x, R = I + sin K + (1-cos) K^2,
+// plus its analytic derivative wrt each component of r (valid through r = 0 thanks to the reference's own +1e-8).
+__device__ void rodrigues_with_grad(const float* r, float* R, float* dR /*[3][9]*/) {
+    const double rx = r[0], ry = r[1], rz = r[2];
+    const double ax = rx + 1e-8, ay = ry + 1e-8, az = rz + 1e-8;
+    const double th = sqrt(ax * ax + ay * ay + az * az);
+    const double s = sin(th), c = cos(th), omc = 1.0 - c;
+    const double rho[3] = {rx / th, ry / th, rz / th};
+    double K[9] = {0, -rho[2], rho[1], rho[2], 0, -rho[0], -rho[1], rho[0], 0};
+    double K2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+    for (int e = 0; e < 9; ++e) R[e] = (float)((e % 4 == 0 ? 1.0 : 0.0) + s * K[e] + omc * K2[e]);
+    const double a3[3] = {ax, ay, az}, r3[3] = {rx, ry, rz};
+    for (int i = 0; i < 3; ++i) {
+        const double thi = a3[i] / th;  // d theta / d r_i
+        double drho[3];
+        for (int k = 0; k < 3; ++k) drho[k] = (k == i ? 1.0 / th : 0.0) - r3[k] * thi / (th * th);
+        const double dK[9] = {0, -drho[2], drho[1], drho[2], 0, -drho[0], -drho[1], drho[0], 0};
+        for (int a = 0; a < 3; ++a)
+            for (int bb = 0; bb < 3; ++bb) {
+                double dKK = 0.0;  // dK K + K dK
+                for (int k = 0; k < 3; ++k) dKK += dK[a * 3 + k] * K[k * 3 + bb] + K[a * 3 + k] * dK[k * 3 + bb];
+                dR[i * 9 + a * 3 + bb] = (float)(c * thi * K[a * 3 + bb] + s * dK[a * 3 + bb] + s * thi * K2[a * 3 + bb] + omc * dKK);
+            }
+    }
+}
+
+struct LmSmem {
+    float J[3 * NM_MAX * LDJ];        // residual Jacobian (rows = 3M)
+    float A[LDJ * LDA];               // J^T J + lambda I  -> Cholesky factor
+    float cmk[NM_MAX * NJ * 3];       // marker transformed by bone k alone
+    float S[NM_MAX * NJ * 3];         // sum over descendants of j of w (c_mk - t_j)
+    float Tv[NM_MAX * 9];             // blended rotation per marker
+    float vp[NM_MAX * 3];             // posed-template marker (before skinning)
+    float res[NM_MAX * 3];            // residual
+    float tgt[NM_MAX * 3];
+    float mask[NM_MAX];
+    float R[NJ * 9], dR[NJ * 27], G[NJ * 12], ta[NJ * 3], Jr[NJ * 3], Om[NJ * 27];
+    float dT[NJ * 30];                // d(posed joint k)/d beta_l
+    float pf[207];
+    float x[DMAX + 3];                // theta[72] | beta[10] | transl[3]
+    float g[LDJ];                     // J^T r  -> solution delta
+    float red[32];
+    float err;
+};
+
+// forward pass at the current parameters: kinematics, marker vertices, residual, error
+__device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
+    const int tid = threadIdx.x, M = Bm.M;
+    float* theta = S.x; float* beta = S.x + 72; float* transl = S.x + 82;
+    if (tid < NJ) {
+        rodrigues_with_grad(theta + tid * 3, S.R + tid * 9, S.dR + tid * 27);
+        if (tid >= 1)
+            for (int e = 0; e < 9; ++e) S.pf[(tid - 1) * 9 + e] = S.R[tid * 9 + e] - (e % 4 == 0 ? 1.f : 0.f);
+    } else if (tid >= 32 && tid < 32 + NJ * 3) {
+        const int o = tid - 32;
+        float v = __ldg(Bm.Jt + o);
+        for (int l = 0; l < 10; ++l) v = fmaf(__ldg(Bm.Js + o * 10 + l), beta[l], v);
+        S.Jr[o] = v;
+    }
+    __syncthreads();
+    if (tid < 32) {  // kinematic chain, one warp, 12 lanes = entries of [R|t]
+        const int r = tid / 4, c = tid % 4;
+        for (int j = 0; j < NJ; ++j) {
+            if (tid < 12) {
+                const int pa = __ldg(Bm.parents + j);
+                float lv;  // local transform entry L[r'][c] needed below is read from R / rel joints
+                if (j == 0) {
+                    lv = c < 3 ? S.R[r * 3 + c] : S.Jr[r];
+                    S.G[r * 4 + c] = lv;
+                } else {
+                    const float* Gp = S.G + pa * 12;
+                    float v = c == 3 ? Gp[r * 4 + 3] : 0.f;
+                    for (int k = 0; k < 3; ++k) {
+                        const float l = c < 3 ? S.R[j * 9 + k * 3 + c] : (S.Jr[j * 3 + k] - S.Jr[pa * 3 + k]);
+                        v = fmaf(Gp[r * 4 + k], l, v);
+                    }
+                    S.G[j * 12 + r * 4 + c] = v;
+                }
+            }
+            __syncwarp();
+        }
+    } else {  // posed-template markers: v_p = T + S beta + P^T pose_feature
+        for (int o = tid - 32; o < M * 3; o += blockDim.x - 32) {
+            float v = __ldg(Bm.Tm + o);
+            for (int l = 0; l < 10; ++l) v = fmaf(__ldg(Bm.Sm + o * 10 + l), beta[l], v);
+            float acc = 0.f;
+            for (int k = 0; k < 207; ++k) acc = fmaf(S.pf[k], __ldg(Bm.Pm + (size_t)k * M * 3 + o), acc);
+            S.vp[o] = v + acc;
+        }
+    }
+    __syncthreads();
+    if (tid < NJ * 3) {  // translation of the relative transform A_j = G_j - [0 | G_j J_j]
+        const int j = tid / 3, c = tid % 3;
+        const float* G = S.G + j * 12;
+        S.ta[tid] = G[c * 4 + 3] - (G[c * 4] * S.Jr[j * 3] + G[c * 4 + 1] * S.Jr[j * 3 + 1] + G[c * 4 + 2] * S.Jr[j * 3 + 2]);
+    }
+    __syncthreads();
+    for (int t = tid; t < M * NJ; t += blockDim.x) {
+        const int m = t / NJ, k = t % NJ;
+        const float* G = S.G + k * 12;
+        const float x = S.vp[m * 3], y = S.vp[m * 3 + 1], z = S.vp[m * 3 + 2];
+        for (int c = 0; c < 3; ++c) S.cmk[t * 3 + c] = fmaf(G[c * 4], x, fmaf(G[c * 4 + 1], y, fmaf(G[c * 4 + 2], z, S.ta[k * 3 + c])));
+    }
+    for (int t = tid; t < M * 9; t += blockDim.x) {
+        const int m = t / 9, e = t % 9;
+        float v = 0.f;
+        for (int k = 0; k < NJ; ++k) v = fmaf(__ldg(Bm.Wm + m * NJ + k), S.G[k * 12 + (e / 3) * 4 + (e % 3)], v);
+        S.Tv[t] = v;
+    }
+    __syncthreads();
+    float e2 = 0.f;
+    for (int o = tid; o < M * 3; o += blockDim.x) {
+        const int m = o / 3, c = o % 3;
+        float v = transl[c];
+        for (int k = 0; k < NJ; ++k) v = fmaf(__ldg(Bm.Wm + m * NJ + k), S.cmk[(m * NJ + k) * 3 + c], v);
+        const float r = S.mask[m] * (S.tgt[o] - v);
+        S.res[o] = r;
+        e2 = fmaf(r, r, e2);
+    }
+    for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    if ((tid & 31) == 0) S.red[tid >> 5] = e2;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += S.red[w];
+        S.err = 0.5f * s;
+    }
+    __syncthreads();
+}
+
+// analytic Jacobian of the residual at the state left by lm_eval; columns: theta(72) | beta(nb) | transl(3)
+__device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
+    const int tid = threadIdx.x, M = Bm.M;
+    const int D = 72 + nb + 3;
+    // Omega_{j,i} = Rg_parent(j) dR_{j,i} Rg_j^T
+    for (int t = tid; t < NJ * 3; t += blockDim.x) {
+        const int j = t / 3;
+        const int pa = __ldg(Bm.parents + j);
+        float tmp[9];
+        const float* dR = S.dR + t * 9;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                float v = 0.f;
+                for (int k = 0; k < 3; ++k) {
+                    const float gp = j == 0 ? (a == k ? 1.f : 0.f) : S.G[pa * 12 + a * 4 + k];
+                    v = fmaf(gp, dR[k * 3 + b], v);
+                }
+                tmp[a * 3 + b] = v;
+            }
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                float v = 0.f;
+                for (int k = 0; k < 3; ++k) v = fmaf(tmp[a * 3 + k], S.G[j * 12 + b * 4 + k], v);
+                S.Om[t * 9 + a * 3 + b] = v;
+            }
+    }
+    // d(posed joint k)/d beta_l : chain over k for each (l, c)
+    for (int t = tid; t < nb * 3; t += blockDim.x) {
+        const int l = t / 3, c = t % 3;
+        for (int k = 0; k < NJ; ++k) {
+            const int pa = __ldg(Bm.parents + k);
+            float v;
+            if (k == 0) v = __ldg(Bm.Js + (0 * 3 + c) * 10 + l);
+            else {
+                v = S.dT[pa * 30 + l * 3 + c];
+                for (int q = 0; q < 3; ++q)
+                    v = fmaf(S.G[pa * 12 + c * 4 + q], __ldg(Bm.Js + (k * 3 + q) * 10 + l) - __ldg(Bm.Js + (pa * 3 + q) * 10 + l), v);
+            }
+            S.dT[k * 30 + l * 3 + c] = v;
+        }
+    }
+    // S[m][j] = sum_{k in desc(j)} w_mk (c_mk - t_j)
+    for (int t = tid; t < M * NJ; t += blockDim.x) {
+        const int m = t / NJ, j = t % NJ;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        const float tx = S.G[j * 12 + 3], ty = S.G[j * 12 + 7], tz = S.G[j * 12 + 11];
+        for (int k = j; k < NJ; ++k) {
+            if ((__ldg(Bm.ancmask + k) >> j) & 1u) {
+                const float w = __ldg(Bm.Wm + m * NJ + k);
+                if (w != 0.f) {
+                    const float* c = S.cmk + (m * NJ + k) * 3;
+                    sx = fmaf(w, c[0] - tx, sx); sy = fmaf(w, c[1] - ty, sy); sz = fmaf(w, c[2] - tz, sz);
+                }
+            }
+        }
+        S.S[t * 3] = sx; S.S[t * 3 + 1] = sy; S.S[t * 3 + 2] = sz;
+    }
+    __syncthreads();
+    // theta columns
+    for (int t = tid; t < M * NJ * 3; t += blockDim.x) {
+        const int m = t / (NJ * 3), ji = t % (NJ * 3), j = ji / 3;
+        const float mk = S.mask[m];
+        float d[3] = {0.f, 0.f, 0.f};
+        if (mk != 0.f) {
+            const float* Om = S.Om + ji * 9;
+            const float* sv = S.S + (m * NJ + j) * 3;
+            for (int c = 0; c < 3; ++c) d[c] = Om[c * 3] * sv[0] + Om[c * 3 + 1] * sv[1] + Om[c * 3 + 2] * sv[2];
+            if (j >= 1) {
+                const float* dR = S.dR + ji * 9;
+                float q[3] = {0.f, 0.f, 0.f};
+                for (int e = 0; e < 9; ++e) {
+                    const float* prow = Bm.Pm + (size_t)((j - 1) * 9 + e) * M * 3 + m * 3;
+                    const float de = dR[e];
+                    q[0] = fmaf(de, __ldg(prow), q[0]); q[1] = fmaf(de, __ldg(prow + 1), q[1]); q[2] = fmaf(de, __ldg(prow + 2), q[2]);
+                }
+                const float* Tv = S.Tv + m * 9;
+                for (int c = 0; c < 3; ++c) d[c] += Tv[c * 3] * q[0] + Tv[c * 3 + 1] * q[1] + Tv[c * 3 + 2] * q[2];
+            }
+        }
+        for (int c = 0; c < 3; ++c) S.J[(m * 3 + c) * LDJ + ji] = -mk * d[c];
+    }
+    // beta columns
+    for (int t = tid; t < M * nb; t += blockDim.x) {
+        const int m = t / nb, l = t % nb;
+        const float mk = S.mask[m];
+        float d[3] = {0.f, 0.f, 0.f};
+        if (mk != 0.f) {
+            const float s0 = __ldg(Bm.Sm + (m * 3 + 0) * 10 + l), s1 = __ldg(Bm.Sm + (m * 3 + 1) * 10 + l), s2 = __ldg(Bm.Sm + (m * 3 + 2) * 10 + l);
+            for (int k = 0; k < NJ; ++k) {
+                const float w = __ldg(Bm.Wm + m * NJ + k);
+                if (w == 0.f) continue;
+                const float a0 = s0 - __ldg(Bm.Js + (k * 3 + 0) * 10 + l), a1 = s1 - __ldg(Bm.Js + (k * 3 + 1) * 10 + l),
+                            a2 = s2 - __ldg(Bm.Js + (k * 3 + 2) * 10 + l);
+                const float* G = S.G + k * 12;
+                for (int c = 0; c < 3; ++c)
+                    d[c] = fmaf(w, G[c * 4] * a0 + G[c * 4 + 1] * a1 + G[c * 4 + 2] * a2 + S.dT[k * 30 + l * 3 + c], d[c]);
+            }
+        }
+        for (int c = 0; c < 3; ++c) S.J[(m * 3 + c) * LDJ + 72 + l] = -mk * d[c];
+    }
+    // translation columns
+    for (int t = tid; t < M * 9; t += blockDim.x) {
+        const int m = t / 9, c = (t % 9) / 3, c2 = t % 3;
+        S.J[(m * 3 + c) * LDJ + 72 + nb + c2] = c == c2 ? -S.mask[m] : 0.f;
+    }
+    (void)D;
+    __syncthreads();
+}
+
+// delta = (J^T J + lambda I)^-1 (-J^T r) by dense Cholesky; result in S.g[0..D)
+__device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
+    const int tid = threadIdx.x;
+    // A = J^T J (6x6 register tiles over the lower triangle incl. diagonal tiles)
+    const int nt = (D + 5) / 6;
+    for (int tile = tid; tile < nt * nt; tile += blockDim.x) {
+        const int ta = tile / nt, tb = tile % nt;
+        if (tb > ta) continue;
+        float acc[6][6];
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            const float* row = S.J + r * LDJ;
+            float a[6], b[6];
+            for (int i = 0; i < 6; ++i) { a[i] = ta * 6 + i < D ? row[ta * 6 + i] : 0.f; b[i] = tb * 6 + i < D ? row[tb * 6 + i] : 0.f; }
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+                const int ia = ta * 6 + i, ib = tb * 6 + j;
+                if (ia < D && ib < D) {
+                    const float v = acc[i][j] + (ia == ib ? lambda : 0.f);
+                    S.A[ia * LDA + ib] = v;
+                    S.A[ib * LDA + ia] = v;
+                }
+            }
+    }
+    for (int a = tid; a < D; a += blockDim.x) {
+        float v = 0.f;
+        for (int r = 0; r < rows; ++r) v = fmaf(S.J[r * LDJ + a], S.res[r], v);
+        S.g[a] = -v;
+    }
+    __syncthreads();
+    // Cholesky A = L L^T (right-looking, lower triangle in place)
+    for (int k = 0; k < D; ++k) {
+        if (tid == 0) S.A[k * LDA + k] = sqrtf(S.A[k * LDA + k]);
+        __syncthreads();
+        const float inv = 1.0f / S.A[k * LDA + k];
+        for (int i = k + 1 + tid; i < D; i += blockDim.x) S.A[i * LDA + k] *= inv;
+        __syncthreads();
+        const int n = D - k - 1;
+        for (int t = tid; t < n * n; t += blockDim.x) {
+            const int i = k + 1 + t / n, j = k + 1 + t % n;
+            if (j <= i) S.A[i * LDA + j] = fmaf(-S.A[i * LDA + k], S.A[j * LDA + k], S.A[i * LDA + j]);
+        }
+        __syncthreads();
+    }
+    // forward / backward substitution (one warp)
+    if (tid < 32) {
+        for (int i = 0; i < D; ++i) {
+            float s = 0.f;
+            for (int k = tid; k < i; k += 32) s = fmaf(S.A[i * LDA + k], S.g[k], s);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) S.g[i] = (S.g[i] - s) / S.A[i * LDA + i];
+            __syncwarp();
+        }
+        for (int i = D - 1; i >= 0; --i) {
+            float s = 0.f;
+            for (int k = i + 1 + tid; k < D; k += 32) s = fmaf(S.A[k * LDA + i], S.g[k], s);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) S.g[i] = (S.g[i] - s) / S.A[i * LDA + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict__ markers, const unsigned char* __restrict__ valid,
+                                                        BodyMarkers Bm, int it0, int it1, float step0, float step1,
+                                                        float damp0, float damp1, float* __restrict__ params,
+                                                        int* __restrict__ iters, float* __restrict__ errs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LmSmem& S = *reinterpret_cast<LmSmem*>(smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x, M = Bm.M;
+    for (int i = tid; i < DMAX + 3; i += blockDim.x) S.x[i] = 0.f;
+    for (int i = tid; i < M * 3; i += blockDim.x) S.tgt[i] = __ldg(markers + (size_t)b * M * 3 + i);
+    for (int i = tid; i < M; i += blockDim.x) S.mask[i] = valid[(size_t)b * M + i] ? 1.f : 0.f;
+    __syncthreads();
+    for (int stage = 0; stage < 2; ++stage) {
+        const int nb = stage == 0 ? 2 : 10;
+        const int D = 72 + nb + 3;
+        const int maxit = stage == 0 ? it0 : it1;
+        const float step = stage == 0 ? step0 : step1, lambda = stage == 0 ? damp0 : damp1;
+        lm_eval(S, Bm);
+        float last = S.err;
+        int done = 0;
+        for (int it = 0; it < maxit; ++it) {
+            lm_jacobian(S, Bm, nb);
+            lm_solve(S, M * 3, D, lambda);
+            // x <- x + step * delta   (columns: theta | beta[0..nb) | transl)
+            for (int a = tid; a < D; a += blockDim.x) {
+                const int xi = a < 72 ? a : (a < 72 + nb ? a : 82 + (a - 72 - nb));
+                S.x[xi] = fmaf(step, S.g[a], S.x[xi]);
+            }
+            __syncthreads();
+            lm_eval(S, Bm);
+            const float err = S.err;
+            done = it + 1;
+            const float ae = fabsf(last - err);
+            const bool conv = (fabsf(err) < 1e-10f) || (ae < 1e-10f) || (ae / last < 1e-8f);
+            if (conv) break;
+            last = err;
+        }
+        if (tid == 0) { iters[b * 2 + stage] = done; errs[b * 2 + stage] = S.err; }
+        __syncthreads();
+    }
+    for (int i = tid; i < DMAX; i += blockDim.x) params[(size_t)b * DMAX + i] = S.x[i];
+}
+
+// ------------------------------------------------------------------------------------------------ full-mesh LBS
+struct BodyFull {
+    const float* v_template;  // [V][3]
+    const float* shapedirs;   // [V][3][10]
+    const float* posedirs;    // [207][V*3]
+    const float* weights;     // [V][24]
+    const float* Jt;          // [24][3]
+    const float* Js;          // [24][3][10]
+    const int* parents;       // [24]
+    const int* extra_vids;    // [21]
+    int V;
+};
+
+// params [B][85] = theta(72: orient, pose) | beta(10) | transl(3)  ->  verts [B][V][3], joints [B][45][3]
+__global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ params, BodyFull Bf, float* __restrict__ verts,
+                                                  float* __restrict__ joints) {
+    __shared__ float sR[NJ * 9], sG[NJ * 12], sA[NJ * 12], sJ[NJ * 3], spf[207], sx[DMAX];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int i = tid; i < DMAX; i += 256) sx[i] = __ldg(params + (size_t)b * DMAX + i);
+    __syncthreads();
+    if (tid < NJ) {
+        float dR[27];
+        rodrigues_with_grad(sx + tid * 3, sR + tid * 9, dR);
+        if (tid >= 1)
+            for (int e = 0; e < 9; ++e) spf[(tid - 1) * 9 + e] = sR[tid * 9 + e] - (e % 4 == 0 ? 1.f : 0.f);
+    } else if (tid >= 32 && tid < 32 + NJ * 3) {
+        const int o = tid - 32;
+        float v = __ldg(Bf.Jt + o);
+        for (int l = 0; l < 10; ++l) v = fmaf(__ldg(Bf.Js + o * 10 + l), sx[72 + l], v);
+        sJ[o] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int j = 0; j < NJ; ++j) {
+            const int pa = Bf.parents[j];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 4; ++c) {
+                    float v;
+                    if (j == 0) v = c < 3 ? sR[r * 3 + c] : sJ[r];
+                    else {
+                        v = c == 3 ? sG[pa * 12 + r * 4 + 3] : 0.f;
+                        for (int k = 0; k < 3; ++k) {
+                            const float l = c < 3 ? sR[j * 9 + k * 3 + c] : (sJ[j * 3 + k] - sJ[pa * 3 + k]);
+                            v = fmaf(sG[pa * 12 + r * 4 + k], l, v);
+                        }
+                    }
+                    sG[j * 12 + r * 4 + c] = v;
+                }
+        }
+        for (int j = 0; j < NJ; ++j)
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) sA[j * 12 + r * 4 + c] = sG[j * 12 + r * 4 + c];
+                sA[j * 12 + r * 4 + 3] = sG[j * 12 + r * 4 + 3] -
+                    (sG[j * 12 + r * 4] * sJ[j * 3] + sG[j * 12 + r * 4 + 1] * sJ[j * 3 + 1] + sG[j * 12 + r * 4 + 2] * sJ[j * 3 + 2]);
+            }
+    }
+    __syncthreads();
+    const int V = Bf.V;
+    if (blockIdx.x == 0 && tid < NJ * 3)
+        joints[((size_t)b * 45 + tid / 3) * 3 + tid % 3] = sG[(tid / 3) * 12 + (tid % 3) * 4 + 3] + sx[82 + tid % 3];
+    for (int v = blockIdx.x * 256 + tid; v < V; v += gridDim.x * 256) {
+        float vp[3];
+        for (int c = 0; c < 3; ++c) {
+            float a = __ldg(Bf.v_template + v * 3 + c);
+            for (int l = 0; l < 10; ++l) a = fmaf(__ldg(Bf.shapedirs + (v * 3 + c) * 10 + l), sx[72 + l], a);
+            float acc = 0.f;
+            for (int k = 0; k < 207; ++k) acc = fmaf(spf[k], __ldg(Bf.posedirs + (size_t)k * V * 3 + v * 3 + c), acc);
+            vp[c] = a + acc;
+        }
+        float T[12];
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        for (int k = 0; k < NJ; ++k) {
+            const float w = __ldg(Bf.weights + v * NJ + k);
+            if (w != 0.f)
+                for (int e = 0; e < 12; ++e) T[e] = fmaf(w, sA[k * 12 + e], T[e]);
+        }
+        for (int c = 0; c < 3; ++c) {
+            const float o = T[c * 4] * vp[0] + T[c * 4 + 1] * vp[1] + T[c * 4 + 2] * vp[2] + T[c * 4 + 3] + sx[82 + c];
+            verts[((size_t)b * V + v) * 3 + c] = o;
+        }
+    }
+}
+
+__global__ void extra_joints_kernel(const float* __restrict__ verts, const int* __restrict__ extra_vids, int V,
+                                    float* __restrict__ joints) {
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < 21 * 3) joints[((size_t)b * 45 + 24 + t / 3) * 3 + t % 3] = verts[((size_t)b * V + extra_vids[t / 3]) * 3 + t % 3];
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+// get_markers (src/models/fit_SMPL.py:17-62). labels int64 [B,N], conf [B,N], inner [B,N,3] -> markers [B,M,3], valid [B,M] u8
+ETCH_API int etch_markers_top3(const float* inner, const long long* labels, const float* conf, int B, int N, int M,
+                               float* markers, unsigned char* valid, cudaStream_t stream) {
+    if (!inner || !labels || !conf || !markers || !valid || B <= 0 || N <= 0 || M <= 0) return ETCH_EINVAL;
+    dim3 grid(etch_cdiv(M, 8), B);
+    markers_kernel<<<grid, 256, 0, stream>>>(inner, labels, conf, N, M, markers, valid);
+    ETCH_RETURN_LAST();
+}
+
+// Two-stage LM marker fit (fit_SMPL.py:157-255 with theseus semantics). params out: [B][85] = orient(3)|pose(69)|betas(10)|transl(3)
+ETCH_API int etch_lm_fit(const float* markers, const unsigned char* valid, const float* Tm, const float* Sm, const float* Pm,
+                         const float* Wm, const float* Jt, const float* Js, const int* parents, const unsigned* ancmask,
+                         int B, int M, int steps0, int steps1, float step0, float step1, float damp0, float damp1,
+                         float* params, int* iters, float* errs, cudaStream_t stream) {
+    if (!markers || !valid || !Tm || !Sm || !Pm || !Wm || !Jt || !Js || !parents || !ancmask || !params || !iters || !errs ||
+        B <= 0 || M <= 0 || M > NM_MAX)
+        return ETCH_EINVAL;
+    BodyMarkers Bm{Tm, Sm, Pm, Wm, Jt, Js, parents, ancmask, M};
+    const size_t smem = sizeof(LmSmem);
+    ETCH_TRY(cudaFuncSetAttribute(lm_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lm_fit_kernel<<<B, 256, smem, stream>>>(markers, valid, Bm, steps0, steps1, step0, step1, damp0, damp1, params, iters, errs);
+    ETCH_RETURN_LAST();
+}
+
+// SMPL forward for the fitted parameters (fit_SMPL.py:257-258): verts [B,V,3], joints [B,45,3] (translation applied)
+ETCH_API int etch_lbs_forward(const float* params, const float* v_template, const float* shapedirs, const float* posedirs,
+                              const float* weights, const float* Jt, const float* Js, const int* parents,
+                              const int* extra_vids, int B, int V, float* verts, float* joints, cudaStream_t stream) {
+    if (!params || !v_template || !shapedirs || !posedirs || !weights || !Jt || !Js || !parents || !extra_vids || !verts || !joints)
+        return ETCH_EINVAL;
+    BodyFull Bf{v_template, shapedirs, posedirs, weights, Jt, Js, parents, extra_vids, V};
+    dim3 grid(etch_cdiv(V, 256), B);
+    lbs_kernel<<<grid, 256, 0, stream>>>(params, Bf, verts, joints);
+    extra_joints_kernel<<<B, 64, 0, stream>>>(verts, extra_vids, V, joints);
+    ETCH_RETURN_LAST();
+}

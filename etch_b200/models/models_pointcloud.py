@@ -1,0 +1,119 @@
+"""Drop-in for the reference's ``models.models_pointcloud`` (src/models/models_pointcloud.py:18-221).
+
+``GT_network_equiv(option)`` keeps the reference's constructor contract (reads ``option.output_folder``,
+``EPN_input_radius``, ``EPN_layer_num``, ``markerset``; writes ``EPN_model_setting_json``), its state-dict key layout
+(so ``load_state_dict(torch.load(ckpt))`` works on reference checkpoints) and its ``forward`` signature/outputs.  The
+arithmetic runs in libetch_b200.so on the current CUDA stream; there is no CPU path (a CPU tensor raises).
+"""
+import json
+import os
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from . import encoder as enc
+from . import heads, spec
+
+
+class GT_network_equiv(nn.Module):
+    def __init__(self, option=None):
+        super().__init__()
+        self.option = option
+        n_layers = int(option.EPN_layer_num)
+        radius = float(option.EPN_input_radius)
+        self._radius, self._n_layers = radius, n_layers
+        self._n_markers = len(option.markerset)
+        tree = spec.ParamTree(spec.network_spec(self._n_markers, radius, n_layers))
+        for name, child in tree.named_children():
+            self.add_module(name, child)
+        spec.xavier_reset_(self)  # models_pointcloud.py:72-77
+        self.standard_vector = torch.tensor([0, 0, 1], dtype=torch.float32)
+        self._plan = None
+        out_dir = getattr(option, "output_folder", None)
+        if out_dir:  # so3net.py:147-149 dumps the layer parameters next to the results
+            try:
+                os.makedirs(out_dir, exist_ok=True)
+                params = {"name": "Invariant SPConv Model", "na": 60, "backbone": [
+                    [{"type": "separable_block", "args": {k: v for k, v in lp.items() if k not in ("block", "conv")}}
+                     for lp in spec.epn_layers(radius, n_layers) if lp["block"] == b] for b in range(n_layers)]}
+                with open(os.path.join(out_dir, "EPN_model_setting_json"), "w") as fh:
+                    json.dump(params, fh)
+            except OSError:
+                pass
+        print(f"====== Using Total {self._n_markers} Markers ======")
+
+    # -- plan cache ------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def _get_plan(self, device):
+        if self._plan is None or self._plan["device"] != device:
+            sd = self.state_dict()
+            e = enc.EncoderPlan(sd, device, self._radius, self._n_layers)
+            self._plan = dict(device=device, enc=e, dir=heads.DirectionPlan(sd, device, e.anchors),
+                              conf=heads.PTPlan(sd, "confidence_encoder.", device),
+                              mag=heads.PTPlan(sd, "magnitude_encoder.", device))
+        return self._plan
+
+    # -- forward ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, hitpts, pred_items=["direction", "magnitude"], direction_mode="standard_vector", _trace=None):
+        """hitpts [B,N,3] (CUDA, fp32) -> ({"confidences" [B,N,1], "part_labels" [B,N,K], "direction" [B,N,3],
+        "magnitude" [B,N,1]}, selected_indexs [B,N,3] int64)."""
+        if not hitpts.is_cuda:
+            raise RuntimeError("etch_b200 has no CPU path: hitpts must be a CUDA tensor")
+        if direction_mode != "standard_vector":
+            raise AssertionError("Not implemented")  # models_pointcloud.py:199-210
+        B, N, _ = hitpts.shape
+        dev = hitpts.device
+        plan = self._get_plan(dev)
+        pts = hitpts.detach().to(torch.float32).contiguous()
+        xyz0 = pts.permute(0, 2, 1).contiguous()
+        etrace = [] if _trace is not None else None
+        xyz2, feats2 = enc.run_encoder(plan["enc"], xyz0, etrace)
+        direction, inv, anc_w, up_idx, up_w = heads.run_direction(plan["dir"], pts, xyz2, feats2, _trace is not None)
+        results = {}
+        need_pt = ("confidence" in pred_items) or ("magnitude" in pred_items)
+        if need_pt:
+            p0 = pts.view(B * N, 3)
+            geo = heads.PTGeometry(p0, B, N)
+            x = inv.view(B * N, -1)
+        if "confidence" in pred_items:
+            xc, logits, conf = heads.run_point_transformer(plan["conf"], geo, x)
+            results["confidences"] = conf.view(B, N, 1)
+            results["part_labels"] = logits.view(B, N, -1)
+        if "direction" in pred_items:
+            results["direction"] = direction
+        if "magnitude" in pred_items:
+            xm, mag = heads.run_point_transformer(plan["mag"], geo, x)
+            results["magnitude"] = mag.view(B, N, 1)
+        if _trace is not None:
+            _trace.update(enc=etrace, inv=inv, anc_w=anc_w, up_idx=up_idx, up_w=up_w, xyz2=xyz2, feats2=feats2)
+            if need_pt:
+                _trace.update(geo=geo)
+            if "confidence" in pred_items:
+                _trace.update(xc=xc)
+            if "magnitude" in pred_items:
+                _trace.update(xm=xm)
+        selected_indexs = torch.arange(0, N, device=dev).repeat(B, 1).unsqueeze(-1).expand(-1, -1, 3)
+        return results, selected_indexs
+
+    @torch.no_grad()
+    def postprocess(self, hitpts, results, scale_magnitude=10.0):
+        """labels = argmax, tightness vector = dir*mag/scale, inner = p - vec (src/eval.py:103,116,183) in one launch."""
+        B, N, _ = hitpts.shape
+        dev = hitpts.device
+        K = results["part_labels"].shape[-1]
+        labels = torch.empty(B, N, dtype=torch.int64, device=dev)
+        vec = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+        inner = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+        L.call("postprocess", L.ptr(hitpts.contiguous()), L.ptr(results["part_labels"].contiguous()),
+               L.ptr(results["direction"].contiguous()), L.ptr(results["magnitude"].contiguous()), B * N, K,
+               L.f32(scale_magnitude), L.ptr(labels), L.ptr(vec), L.ptr(inner))
+        return labels, vec, inner

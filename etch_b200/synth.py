@@ -31,7 +31,7 @@ def sample_scans(B, n, seed=0):
     return np.stack([sample_scan(n, seed * 1000 + b) for b in range(B)], 0)
 
 
-def make_state_dict(seed=1, n_markers=86, attention_gain=6.0):
+def make_state_dict(seed=1, n_markers=86, attention_gain=2.0):
     g = torch.Generator().manual_seed(seed)
     torch_state = torch.random.get_rng_state()
     torch.manual_seed(seed)

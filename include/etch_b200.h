@@ -1,0 +1,148 @@
+/*
+ * etch_b200.h -- C ABI of libetch_b200.so: the B200-native (sm_100a) implementation of ETCH's per-scan
+ * inference-and-fit hot path.
+ *
+ * Conventions (every entry point):
+ *   - extern "C", plain device pointers + sizes, no torch types; caller owns all memory; nothing is allocated inside;
+ *   - returns 0 on success, a positive cudaError_t on a CUDA failure, ETCH_EINVAL (-1) on a bad argument;
+ *   - work is enqueued on `stream` and the call returns immediately (no host synchronisation);
+ *   - re-entrant and thread-safe (no global state); pointers must be device memory of the current device, fp32
+ *     tensors contiguous in the stated layout.
+ * File:line citations refer to the reference tree (boqian-li/ETCH) and name the interface each entry replaces.
+ * INTEGRATION.md shows the reference-side binding (pybind/ctypes stub) a maintainer would add.
+ */
+#ifndef ETCH_B200_H
+#define ETCH_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETCH_OK 0
+#define ETCH_EINVAL (-1)
+#define ETCH_EUNSUPPORTED (-2)
+
+/* ---- native extension entry points of the reference (boundary B2) ------------------------- */
+
+/* epn_grouping.furthest_point_sampling   external/vgtk/vgtk/cuda/grouping_cuda.cpp:160-174 (kernel grouping_cuda_kernel.cu:351-466)
+ * xyz [B,3,n] -> idx [B,m]; start index 0, points with |p|^2 <= 1e-3 skipped, reference tie rule reproduced. n <= 28672. */
+int etch_fps_bcn(const float* xyz, int B, int n, int m, int* idx, cudaStream_t stream);
+
+/* pointops_cuda.furthestsampling_cuda    external/pointops/src/sampling/sampling_cuda.cpp:8-16 (kernel sampling_cuda_kernel.cu:15-129)
+ * packed xyz [n,3], cumulative offset/new_offset [b] -> idx [new_offset[b-1]] (global row ids). tmp is unused (may be NULL). */
+int etch_fps_packed(int b, int n_max, const float* xyz, const int* offset, const int* new_offset, float* tmp, int* idx,
+                    cudaStream_t stream);
+
+/* epn_grouping.ball_query                external/vgtk/vgtk/cuda/grouping_cuda.cpp:71-86 (kernel grouping_cuda_kernel.cu:67-113)
+ * new_xyz [B,3,m], xyz [B,3,n] -> idx [B,m,nsample] (first-nsample-in-index-order, cyclic padding, zero last slot quirk). */
+int etch_ball_query_bcn(const float* new_xyz, const float* xyz, int B, int m, int n, float radius, int nsample, int* idx,
+                        cudaStream_t stream);
+
+/* epn_gathering.gather_points_forward    external/vgtk/vgtk/cuda/gathering_cuda.cpp:29-43 (kernel gathering_cuda_kernel.cu:42-68)
+ * points [B,C,n], idx [B,m] -> out [B,C,m]. */
+int etch_gather_bcn(const float* points, const int* idx, int B, int C, int n, int m, float* out, cudaStream_t stream);
+
+/* pointops_cuda.knnquery_cuda            external/pointops/src/knnquery/knnquery_cuda.cpp:8-17 (kernel knnquery_cuda_kernel.cu:65-108)
+ * xyz [n,3], new_xyz [m,3], offsets [nbatch] -> idx [m,nsample], dist2 [m,nsample] ascending; nsample <= 100. */
+int etch_knn_packed(int m, int nsample, const float* xyz, const float* new_xyz, const int* offset, const int* new_offset,
+                    int nbatch, int* idx, float* dist2, cudaStream_t stream);
+
+/* block-size rule of the reference launchers (grouping_cuda_kernel.cu:29-33): 2^floor(log2 n) capped at 1024 */
+int etch_opt_threads(int work_size);
+
+/* ---- fused operators behind the Python operator API (boundary B1: models.models_pointcloud / models.fit_SMPL) ---- */
+/* Encoder features are point-major: feat [B, P, 60, C].  `stats` buffers are [B][C][2] doubles (sum, sum of squares),
+ * zeroed by the caller, accumulated by the producer and consumed (as InstanceNorm mean / rstd) by the next kernel.   */
+
+/* InterSO3Conv for the first conv (c_in = 1, constant occupancy feature): fused kernel-weight generation + BasicSO3Conv.
+ * vgtk/so3conv/modules.py:120-128,33-39; functional.py:286-324,61-67.  kr [60,24,3] = R_a k; Wt [24][cout]. */
+int etch_so3_inter_conv_c1(const float* xyz, const int* sample_idx, const int* nbr, const float* kr, const float* Wt,
+                           const float* bias, int B, int q, int P, int nn, int cout, float sigma, float* zraw,
+                           double* stats, cudaStream_t stream);
+
+/* InterSO3Conv, c_in in {32,64}: same fusion plus the neighbour-feature contraction (einsum 'bcpna,bpakn->bckpa').
+ * krs [60,24,4] = {2/sigma * R_a k, |R_a k|^2 / sigma}; Wt [cin*24][cout] (row c*24+k). */
+int etch_so3_inter_conv(const float* xyz, const float* feat, const int* sample_idx, const int* nbr, const float* krs,
+                        const float* Wt, const float* bias, int B, int q, int P, int nn, int cin, int cout, float sigma,
+                        float* zraw, double* stats, cudaStream_t stream);
+
+/* IntraSO3Conv applied to leaky_relu(InstanceNorm(zin)) (norm folded into the load).  modules.py:131-153; functional.py:331-343;
+ * src/models/so3conv.py:36-44.  intra_idx [60,12] int32; Wt [12][c][cout]. */
+int etch_so3_intra_conv(const float* zin, const double* in_stats, const int* intra_idx, const float* Wt, const float* bias,
+                        int B, int P, int c, int cout, float* zraw, double* stats, cudaStream_t stream);
+
+/* skip branch: Conv2d 1x1 on feats[:, :, sample_idx] (src/models/so3conv.py:178-180).  Wt [cin][cout]; ident = arange(60). */
+int etch_so3_skip_conv(const float* feat, const int* sample_idx, const int* ident, const float* Wt, const float* bias, int B,
+                       int q, int P, int cin, int cout, float* zraw, double* stats, cudaStream_t stream);
+
+/* block output = leaky_relu(IN(z_intra)) + leaky_relu(IN(z_skip))  (src/models/so3conv.py:181-182); z_skip may be NULL. */
+int etch_so3_combine(const float* z_intra, const double* s_intra, const float* z_skip, const double* s_skip, int B, int P,
+                     int c, float* out, cudaStream_t stream);
+
+/* PointFeatPropagation's 3-NN search + weights (src/models/pointnet2_utils.py:45-74): fine [B,N,3], coarse [B,3,S]. */
+int etch_upsample3(const float* fine_bn3, const float* coarse_b3s, int B, int N, int S, int* idx, float* w,
+                   cudaStream_t stream);
+
+/* feature propagation + anchor mean + decode_direction (models_pointcloud.py:111-126,181-184; direction_backbones.py:129-223;
+ * src/models/so3conv.py:186-225).  Weight tensors are the host-folded forms documented in etch_b200/models/heads.py. */
+int etch_direction_head(const float* feats, const int* up_idx, const float* up_w, const float* Wqkv1, const float* Wc1,
+                        const float* bc1, const float* Wqkv2, const float* Wf, const float* bf, const float* vreg,
+                        float creg, const float* anchors, int B, int N, int S, float* dir, float* inv, float* anc_w,
+                        cudaStream_t stream);
+
+/* nn.Linear / Conv1d(k=1) + eval BatchNorm1d + ReLU + residual (+ per-segment row bias) in one launch
+ * (pointtransformer_seg.py:40-51,71-80,101-112,144-145).  Y = relu?((X Wt + seg) * scale + shift + R). */
+int etch_linear(const float* X, int ldx, const float* Wt, int n, int ci, int co, const float* scale, const float* shift,
+                const float* R, const float* seg, const int* seg_off, int nseg, int relu, float* Y, int ldy,
+                cudaStream_t stream);
+
+/* PointTransformerLayer.forward after the q/k/v projections + bn2 + ReLU (pointtransformer_seg.py:24-37,118). */
+int etch_pt_attention(const float* p, const float* qkv, const int* idx, const float* P0, const float* p0b, const float* P3,
+                      const float* p3b, const float* s0, const float* h0, const float* W1, const float* b1, const float* W2,
+                      const float* b2, const float* so, const float* ho, int n, int ns, int c, float* out,
+                      cudaStream_t stream);
+
+/* TransitionDown (stride 4) grouping + BN + ReLU + MaxPool (pointtransformer_seg.py:59-66). */
+int etch_pt_down_pool(const float* p, const float* new_p, const float* Yx, const int* idx, const float* Wp, const float* scale,
+                      const float* shift, int m, int ns, int co, float* out, cudaStream_t stream);
+
+/* TransitionUp: linear1(x1) + pointops.interpolation(...) (pointtransformer_seg.py:96-97; src/models/pointops.py:164-178). */
+int etch_pt_interp_add(const float* a, const float* f, const int* idx, const float* d2, int n, int c, float* out,
+                       cudaStream_t stream);
+
+/* per-scan mean of packed rows (TransitionUp head, pointtransformer_seg.py:84-92). */
+int etch_seg_mean(const float* x, const int* off, int nseg, int c, float* out, cudaStream_t stream);
+
+/* row gather out[i] = x[idx[i]] (p[idx.long(), :], pointtransformer_seg.py:60). */
+int etch_gather_rows(const float* x, const int* idx, int m, int c, float* out, cudaStream_t stream);
+
+/* confi head + softmax(cls)-weighted confidence without the [B,11008,N] intermediate (pointtransformer_seg.py:145,184-189). */
+int etch_conf_head(const float* x, const float* logits, const float* W0t, const float* b0, const float* w2, const float* b2,
+                   int n, int K, float* conf, cudaStream_t stream);
+
+/* labels = argmax, vec = dir*mag/scale, inner = p - vec (src/eval.py:103,116,183; src/inference_demo.py:52-59). */
+int etch_postprocess(const float* p, const float* logits, const float* dir, const float* mag, int n, int K,
+                     float scale_magnitude, long long* labels, float* vec, float* inner, cudaStream_t stream);
+
+/* get_markers (src/models/fit_SMPL.py:17-62). */
+int etch_markers_top3(const float* inner, const long long* labels, const float* conf, int B, int N, int M, float* markers,
+                      unsigned char* valid, cudaStream_t stream);
+
+/* two-stage Levenberg-Marquardt marker fit (src/models/fit_SMPL.py:157-255; theseus LevenbergMarquardt semantics).
+ * params [B][85] = global_orient(3) | body_pose(69) | betas(10) | transl(3); iters/errs [B][2] per stage. */
+int etch_lm_fit(const float* markers, const unsigned char* valid, const float* Tm, const float* Sm, const float* Pm,
+                const float* Wm, const float* Jt, const float* Js, const int* parents, const unsigned* ancmask, int B, int M,
+                int steps0, int steps1, float step0, float step1, float damp0, float damp1, float* params, int* iters,
+                float* errs, cudaStream_t stream);
+
+/* SMPL.forward for fitted parameters (external/smplx/smplx/lbs.py:153-248, body_models.py:386-414). */
+int etch_lbs_forward(const float* params, const float* v_template, const float* shapedirs, const float* posedirs,
+                     const float* weights, const float* Jt, const float* Js, const int* parents, const int* extra_vids, int B,
+                     int V, float* verts, float* joints, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ETCH_B200_H */

@@ -1,0 +1,147 @@
+"""GPU parity of the full network forward (encoder + direction head + both PointTransformers + heads) against
+(a) the torch-CPU oracle stage by stage and (b) the golden outputs of the unmodified reference.
+
+Stated tolerances (fp32 end to end; differences: summation order, BN folding, fused affine maps):
+  activations      : max abs err <= 5e-4 * scale of the tensor
+  part-label argmax: identical except where the top-2 logit gap of the oracle is < 1e-3 (counted and bounded)
+  direction        : where the chordal mean is well conditioned (sigma_2/sigma_1 > 1e-2): 99% of points within 3e-3,
+                     all within 2e-2.  The seeded random checkpoint is far more chaotic than a trained one: a 1e-5
+                     relative perturbation of the encoder output (pure summation-order noise; the torch-CPU oracle and
+                     the reference Python differ by that much from each other) is amplified ~30x by the random softmax
+                     attention before the polar decomposition.
+  tightness vectors: |dir*mag/10| max abs err <= 5e-4 m on this checkpoint (median ~1e-5 m)
+"""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _option():
+    ms = json.load(open(os.path.join(ROOT, "etch_b200", "data", "superset_smpl.json")))
+    return types.SimpleNamespace(output_folder=None, EPN_input_radius=0.4, EPN_layer_num=2, markerset=ms)
+
+
+def _model(cuda):
+    from etch_b200 import synth
+    from etch_b200.models.models_pointcloud import GT_network_equiv
+    sd = synth.make_state_dict(1)
+    net = GT_network_equiv(_option())
+    net.load_state_dict(sd)
+    return net.to(cuda).eval(), sd
+
+
+def _rel(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
+
+
+def _well_conditioned(anc_w):
+    from etch_b200.models import spec
+    anchors = torch.from_numpy(spec.so3_tables()["anchors"])
+    Ce = torch.einsum("...a,aij->...ij", anc_w.cpu(), anchors)
+    sv = torch.linalg.svdvals(Ce)
+    return (sv[..., 1] > 1e-2 * sv[..., 0].clamp_min(1e-12)).numpy()
+
+
+@pytest.mark.parametrize("B,N", [(2, 1024)])
+def test_forward_matches_oracle_stage_by_stage(cuda, B, N):
+    from etch_b200 import synth
+    from etch_b200.models import spec
+    from oracle import net as onet
+    net, sd = _model(cuda)
+    pts = torch.from_numpy(synth.sample_scans(B, N, 21))
+    with torch.no_grad():
+        ref, rt = onet.forward(pts, sd, spec.so3_tables(), return_trace=True)
+    tr = {}
+    out, sel = net(pts.to(cuda), ["confidence", "direction", "magnitude"], "standard_vector", _trace=tr)
+    torch.cuda.synchronize()
+    assert sel.shape == (B, N, 3) and sel.dtype == torch.int64 and (sel[0, :, 0].cpu() == torch.arange(N)).all()
+    # 3-NN propagation: neighbour sets (as sets) and weights
+    gi, ri = np.sort(tr["up_idx"].cpu().numpy(), -1), np.sort(rt["up_idx"].numpy(), -1)
+    same = (gi == ri).all(-1)
+    assert same.mean() > 0.995, "3-NN neighbour sets differ on %.3f%% of points" % (100 * (1 - same.mean()))
+    assert _rel(tr["inv"], rt["inv"]) < 5e-4
+    assert _rel(tr["anc_w"], rt["anc_w"]) < 2e-3
+    ok = _well_conditioned(rt["anc_w"])
+    assert ok.mean() > 0.9
+    derr = (out["direction"].cpu() - ref["direction"]).norm(dim=-1).numpy()
+    assert derr[ok].max() < 2e-2 and np.quantile(derr[ok], 0.99) < 3e-3, (derr[ok].max(), np.quantile(derr[ok], 0.99))
+    assert np.allclose(out["direction"].norm(dim=-1).cpu().numpy(), 1.0, atol=1e-4)
+    # PointTransformer bodies and heads
+    assert _rel(tr["xc"], rt["xc"]) < 1e-3
+    assert _rel(tr["xm"], rt["xm"]) < 1e-3
+    assert _rel(out["part_labels"], ref["part_labels"]) < 1e-3
+    assert _rel(out["confidences"], ref["confidences"]) < 1e-3
+    assert _rel(out["magnitude"], ref["magnitude"]) < 1e-3
+    top2 = ref["part_labels"].topk(2, dim=-1).values
+    gap = (top2[..., 0] - top2[..., 1]).numpy()
+    flips = (out["part_labels"].argmax(-1).cpu() != ref["part_labels"].argmax(-1)).numpy()
+    assert not (flips & (gap > 1e-3)).any(), "argmax flipped on a clear margin"
+    assert flips.mean() < 0.01
+    # post-processing kernel
+    labels, vec, inner = net.postprocess(pts.to(cuda), out)
+    assert (labels.cpu() == out["part_labels"].argmax(-1).cpu()).all()
+    v_ref = out["direction"] * out["magnitude"] / 10.0
+    assert torch.allclose(vec, v_ref, atol=1e-7) and torch.allclose(inner, pts.to(cuda) - v_ref, atol=1e-6)
+
+
+def test_forward_matches_reference_golden(cuda):
+    """same seeded checkpoint and scan as tools/gen_golden.py ran through the unmodified reference Python."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_net_b2_n600.npz"))
+    net, _ = _model(cuda)
+    tr = {}
+    out, _ = net(torch.from_numpy(g["pts"]).to(cuda), ["confidence", "direction", "magnitude"], "standard_vector", _trace=tr)
+    for k in ("confidences", "part_labels", "magnitude"):
+        assert _rel(out[k], torch.from_numpy(g[k])) < 1e-3, k
+    ref_lab = g["part_labels"].argmax(-1)
+    srt = np.sort(g["part_labels"], -1)
+    gap = srt[..., -1] - srt[..., -2]
+    flips = out["part_labels"].argmax(-1).cpu().numpy() != ref_lab
+    assert not (flips & (gap > 1e-3)).any() and flips.mean() < 0.01
+    ok = _well_conditioned(tr["anc_w"])
+    derr = np.linalg.norm(out["direction"].cpu().numpy() - g["direction"], axis=-1)
+    assert ok.mean() > 0.9 and derr[ok].max() < 2e-2 and np.quantile(derr[ok], 0.99) < 3e-3
+    vec = out["direction"].cpu().numpy() * out["magnitude"].cpu().numpy() / 10.0
+    vref = g["direction"] * g["magnitude"] / 10.0
+    verr = np.abs(vec - vref)[ok]
+    assert verr.max() < 5e-4 and np.median(verr) < 5e-5  # tightness vectors (metres)
+
+
+def test_equivariance_under_icosahedral_rotation(cuda):
+    """size-independent property: rotating the scan by an anchor rotation leaves magnitude /
+    labels / confidence unchanged and rotates the predicted direction."""
+    from etch_b200 import synth
+    from etch_b200.models import spec
+    net, _ = _model(cuda)
+    pts = torch.from_numpy(synth.sample_scans(1, 2000, 33)).to(cuda)
+    R = torch.from_numpy(spec.so3_tables()["anchors"][7]).to(cuda)
+    tr0, tr1 = {}, {}
+    o0, _ = net(pts, ["confidence", "direction", "magnitude"], _trace=tr0)
+    o1, _ = net(pts @ R.t(), ["confidence", "direction", "magnitude"], _trace=tr1)
+    # FPS / ball query are rotation invariant up to fp rounding of distances; compare the smooth outputs loosely
+    assert _rel(tr1["inv"], tr0["inv"]) < 5e-2
+    ok = _well_conditioned(tr0["anc_w"]) & _well_conditioned(tr1["anc_w"])
+    d = (o1["direction"] - o0["direction"] @ R.t()).norm(dim=-1).cpu().numpy()
+    assert np.median(d[ok]) < 5e-2
+
+
+def test_full_size_forward_properties(cuda):
+    """BASELINE config sizes (B=8, N=5000): outputs finite, unit directions, deterministic across two runs."""
+    from etch_b200 import synth
+    net, _ = _model(cuda)
+    pts = torch.from_numpy(synth.sample_scans(8, 5000, 2)).to(cuda)
+    o0, _ = net(pts, ["confidence", "direction", "magnitude"])
+    o1, _ = net(pts, ["confidence", "direction", "magnitude"])
+    for k in o0:
+        assert torch.isfinite(o0[k]).all(), k
+    assert (o0["direction"].norm(dim=-1) - 1).abs().max() < 1e-3
+    # InstanceNorm statistics use double atomics (order-dependent in the last bits): runs agree to fp32 noise
+    assert _rel(o1["part_labels"], o0["part_labels"]) < 1e-4
+    assert o0["part_labels"].shape == (8, 5000, 86)

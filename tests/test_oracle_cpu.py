@@ -1,0 +1,164 @@
+"""CPU suite (-m "not gpu"): pins the oracle against the golden vectors produced from the unmodified reference
+(tools/gen_golden.py), checks host logic and that the C-ABI library loads and exports every declared symbol."""
+import json
+import os
+import re
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _markerset():
+    return json.load(open(os.path.join(ROOT, "etch_b200", "data", "superset_smpl.json")))
+
+
+def test_oracle_network_matches_reference_golden():
+    """oracle/net.py (used as the checker on the GPU box) reproduces the reference forward on the golden scan."""
+    from etch_b200 import synth
+    from etch_b200.models import spec
+    from oracle import net as onet
+    g = np.load(os.path.join(GOLD, "golden_net_b2_n600.npz"))
+    sd = synth.make_state_dict(1)
+    with torch.no_grad():
+        out, tr = onet.forward(torch.from_numpy(g["pts"]), sd, spec.so3_tables(), return_trace=True)
+    for k, tol in [("confidences", 1e-5), ("part_labels", 1e-4), ("magnitude", 1e-4)]:
+        err = np.abs(out[k].numpy() - g[k]).max()
+        assert err < tol * max(1.0, np.abs(g[k]).max()), (k, err)
+    assert (out["part_labels"].argmax(-1).numpy() == g["part_labels"].argmax(-1)).all()
+    # direction: compare where the chordal mean is well conditioned (second singular value of sum_a w_a R_a)
+    anchors = torch.from_numpy(spec.so3_tables()["anchors"])
+    Ce = torch.einsum("bna,aij->bnij", tr["anc_w"], anchors)
+    sv = torch.linalg.svdvals(Ce)
+    ok = (sv[..., 1] > 1e-2 * sv[..., 0].clamp_min(1e-12)).numpy()
+    assert ok.mean() > 0.9
+    derr = np.linalg.norm(out["direction"].numpy() - g["direction"], axis=-1)
+    assert derr[ok].max() < 2e-2 and np.quantile(derr[ok], 0.99) < 3e-3, (derr[ok].max(), np.quantile(derr[ok], 0.99))
+    assert np.allclose(np.linalg.norm(out["direction"].numpy(), axis=-1), 1.0, atol=1e-4)
+
+
+def test_oracle_lbs_matches_reference_golden():
+    from etch_b200 import smpl_model
+    from oracle import smpl as osmpl
+    g = np.load(os.path.join(GOLD, "golden_lbs.npz"))
+    model = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in smpl_model.synthetic_body(0).items()}
+    pose = torch.from_numpy(g["pose"])
+    v, j = osmpl.smpl_forward(model, pose[:, :3], pose[:, 3:], torch.from_numpy(g["betas"]), torch.from_numpy(g["transl"]))
+    assert np.abs(v.numpy() - g["verts"]).max() < 2e-6
+    assert np.abs(j.numpy() - g["joints"]).max() < 2e-6
+
+
+def test_oracle_markers_match_reference_golden():
+    from oracle import lm as olm
+    g = np.load(os.path.join(GOLD, "golden_markers.npz"))
+    mk, valid = olm.get_markers(torch.from_numpy(g["inner"]), torch.from_numpy(g["labels"]), torch.from_numpy(g["conf"]), 86)
+    assert (valid.numpy() == g["valid"]).all()
+    assert np.abs(mk.numpy() - g["markers"]).max() < 1e-5
+
+
+def test_state_dict_layout_is_the_reference_layout():
+    """key names / shapes / dtypes of our module == what the reference module exports (1924 tensors)."""
+    from etch_b200.models import spec
+    tree = spec.ParamTree(spec.network_spec(86))
+    sd = tree.state_dict()
+    assert len(sd) == 1924
+    assert sum(p.numel() for p in tree.parameters()) == 20414422
+    assert sd["encoder.backbone.0.blocks.0.inter_conv.conv.basic_conv.W"].shape == (32, 24)
+    assert sd["encoder.backbone.1.blocks.1.inter_conv.conv.basic_conv.W"].shape == (64, 1536)
+    assert sd["encoder.backbone.0.blocks.0.intra_conv.conv.intra_idx"].dtype == torch.int64
+    assert sd["confidence_encoder.confi.0.weight"].shape == (11008, 128, 1)
+    assert sd["magnitude_encoder.dec5.0.linear1.0.weight"].shape == (512, 1024)
+
+
+def test_so3_tables_are_a_rotation_group():
+    from etch_b200.models import spec
+    t = spec.so3_tables()
+    A, I = t["anchors"].astype(np.float64), t["intra_idx"]
+    assert np.abs(A[29] - np.eye(3)).max() == 0
+    assert np.abs(np.einsum("aij,akj->aik", A, A) - np.eye(3)).max() < 1e-6 and np.allclose(np.linalg.det(A), 1, atol=1e-6)
+    prod = np.einsum("aij,bjk->abik", A, A).reshape(3600, 9)
+    d = np.abs(prod[:, None, :] - A.reshape(1, 60, 9)).max(-1).min(-1)
+    assert d.max() < 1e-5  # closed under multiplication
+    assert (np.sort(I, 1)[:, 1:] != np.sort(I, 1)[:, :-1]).all() and (I[:, 9] == np.arange(60)).all()
+    # equivariance of the table: R_a^T R_{I[a,j]} does not depend on a (same relative rotation for every anchor)
+    rel = np.einsum("aki,ajkl->ajil", A, A[I])  # [60,12,3,3]
+    assert np.abs(rel - rel[0:1]).max() < 1e-5
+
+
+def test_layer_constants_match_reference_build_model():
+    from etch_b200.models import spec
+    ls = spec.epn_layers()
+    assert [(l["dim_in"], l["dim_out"], l["stride"], l["n_neighbor"], l["lazy_sample"]) for l in ls] == [
+        (1, 32, 2, 64, False), (32, 32, 1, 32, True), (32, 64, 2, 64, True), (64, 64, 1, 32, True)]
+    assert np.allclose([l["radius"] for l in ls], [0.08, 0.11313708, 0.16, 0.16])
+    assert np.allclose([l["sigma"] for l in ls], [0.0032, 0.0064, 0.0128, 0.0128])
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from etch_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "etch_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(etch_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    exported = _lib.exported_symbols()
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    lib = _lib.lib()
+    for s in declared:
+        assert hasattr(lib, s)
+    assert lib.etch_opt_threads(5000) == 1024 and lib.etch_opt_threads(600) == 512
+
+
+def test_product_fails_loudly_without_cuda():
+    """no CPU fallback: a CPU tensor is rejected instead of silently computed elsewhere."""
+    from etch_b200.models.models_pointcloud import GT_network_equiv
+    opt = types.SimpleNamespace(output_folder=None, EPN_input_radius=0.4, EPN_layer_num=2, markerset=_markerset())
+    net = GT_network_equiv(opt).eval()
+    try:
+        net(torch.zeros(1, 64, 3), ["direction"])
+    except RuntimeError as e:
+        assert "CUDA" in str(e)
+    else:
+        raise AssertionError("CPU input must raise")
+    from etch_b200.ext import epn_grouping
+    try:
+        epn_grouping.ball_query(torch.zeros(1, 3, 4), torch.zeros(1, 3, 4), 0.1, 2)
+    except RuntimeError:
+        pass
+    else:
+        raise AssertionError("CPU input must raise")
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for d, _, fs in os.walk(os.path.join(ROOT, "etch_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle", txt, re.M) or "libetch_oracle" in txt:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_oracle_index_properties():
+    """size-independent properties of the C oracle itself: FPS yields distinct indices starting at 0; ball-query rows
+    are ascending up to the first repeat; kNN distances ascend and the first self-neighbour is the point itself."""
+    from etch_b200 import synth
+    from oracle import index_ops as O
+    x = np.ascontiguousarray(synth.sample_scans(1, 2000, 3).transpose(0, 2, 1))
+    idx = O.fps_bcn(x, 1000)
+    assert idx[0, 0] == 0 and len(set(idx[0])) == 1000
+    q = O.gather_bcn(x, idx)
+    b = O.ball_query_bcn(q, x, 0.08, 64)[0]
+    for row in b[:50]:
+        k = 1
+        while k < 64 and row[k] > row[k - 1]:
+            k += 1
+        assert (row[k:] == np.resize(row[:k], 64)[k:]).all() or k == 63
+    p = np.ascontiguousarray(x[0].T)
+    off = np.array([2000], np.int32)
+    ki, kd = O.knn_packed(8, p, p, off, off)
+    assert (ki[:, 0] == np.arange(2000)).all() and (np.diff(kd, axis=1) >= 0).all()
