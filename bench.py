@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- scans/sec of ETCH's inference-and-fit hot path (net forward + SMPL marker fit) on N x B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl etch|reference] [--batch 8] [--points 5000]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one batch of B scans per GPU (BASELINE.json configs[1]: 5k-point scans,
+batch 8): network forward (encoder + direction / magnitude / marker-confidence heads), post-processing, marker
+extraction, two-stage Levenberg-Marquardt SMPL fit and the final full-mesh LBS.  Scans are independent, so ranks never
+communicate on the data path (weak scaling); the only collectives are the timing barrier and the max over ranks.
+
+Prints ONE JSON line on rank 0 ("Measurement" for every field).
+  value    device-resident inputs, per-step CUDA-event time, L2 flushed between timed steps, max over ranks
+  e2e      same metric through the public operator API with pinned HOST buffers: H2D of the scans + D2H of the fitted
+           mesh/parameters inside the timed region
+  roofline dominant kernel, timed live with CUDA events on the launching stream in a separate instrumented step
+  cpu_baseline / --impl reference : the CPU oracle (port of the reference's algorithm; the reference has no CPU path and
+           its LM solver is not vendored) timed on this box's host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# algorithmic work of the reference algorithm per 5000-point scan, GFLOP
+ALGO_GFLOP_5K = {
+    "so3_inter_conv": 15.7 + 15.7 + 22.5, "so3_inter_conv_c1": 2.5, "so3_intra_conv": 22.1, "direction_head": 51.0,
+    "conf_head": 14.1,
+}
+
+
+def _markerset():
+    return json.load(open(os.path.join(ROOT, "etch_b200", "data", "superset_smpl.json")))
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"), which="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, which="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def _oracle_scan_step(pts, sd, tables, body_t, vids, n_markers):
+    """one scan through the CPU oracle: network forward + post-processing + markers + 2-stage LM + final LBS."""
+    from oracle import lm as olm
+    from oracle import net as onet
+    with torch.no_grad():
+        out = onet.forward(pts, sd, tables)
+        labels, vec, inner = onet.postprocess(pts, out)
+        mk, valid = olm.get_markers(inner, labels, out["confidences"], n_markers)
+    fit = olm.fit(body_t, vids, mk, valid)
+    return fit["vertices"]
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm on this box's host cores.  The reference has no CPU path and its
+    LM solver (theseus) is not vendored, so this is the oracle port (oracle/, kind = "port"), all host threads."""
+    if rank != 0:
+        return
+    from etch_b200 import smpl_model, synth
+    from etch_b200.models import spec
+    from oracle import index_ops
+    index_ops.lib()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_state_dict(1)
+    tables = spec.so3_tables()
+    ms = _markerset()
+    body = smpl_model.synthetic_body(0)
+    body_t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in body.items()}
+    vids = list(ms.values())
+    budget_s = float(os.environ.get("ETCH_REF_BUDGET_S", "200"))
+    t_start = time.time()
+    times = []
+    warm = min(args.warmup, 1)
+    for i in range(warm + args.steps):
+        pts = torch.from_numpy(synth.sample_scans(1, args.points, 100 + i))
+        t0 = time.time()
+        _oracle_scan_step(pts, sd, tables, body_t, vids, len(ms))
+        dt = time.time() - t0
+        if i >= warm:
+            times.append(dt)
+        if time.time() - t_start + dt > budget_s and len(times) >= 1:
+            break
+    ms_step = 1000.0 * float(np.mean(times))
+    value = 1000.0 / ms_step  # one scan per step
+    sample = "1 scan of %d points per step (net forward + 2-stage LM fit + final LBS), %d timed steps" % (args.points, len(times))
+    line = {"impl": "reference", "metric": "scans/sec (net fwd + SMPL fit)", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "5k-pt clothed scans, net forward + 2-stage LM SMPL fit (BASELINE configs[1])", "points": args.points,
+                       "batch_per_step": 1, "note": "CPU oracle port; requested steps=%d capped by a %ds budget" % (args.steps, int(budget_s))},
+            "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- etch arm
+class Pipeline:
+    """the public operator API of the repo, as a caller of the reference's eval.py would use it."""
+
+    def __init__(self, device):
+        from etch_b200 import smpl_model, synth
+        from etch_b200.models import fit_SMPL
+        from etch_b200.models.models_pointcloud import GT_network_equiv
+        self.ms = _markerset()
+        opt = types.SimpleNamespace(output_folder=None, EPN_input_radius=0.4, EPN_layer_num=2, markerset=self.ms)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            self.net = GT_network_equiv(opt)
+        self.net.load_state_dict(synth.make_state_dict(1))
+        self.net = self.net.to(device).eval()
+        self.args = types.SimpleNamespace(markerset=self.ms, smpl_model=smpl_model.synthetic_body(0), device=str(device))
+        self.fit = fit_SMPL
+        self.tables = fit_SMPL.body_tables(self.args, "neutral", device)
+
+    def step(self, pts):
+        out, _ = self.net(pts, ["confidence", "direction", "magnitude"], "standard_vector")
+        labels, vec, inner = self.net.postprocess(pts, out)
+        markers, valid = self.fit.get_markers(self.args, inner, labels, out["confidences"])
+        return self.fit.lm_fit(self.tables, markers, valid)
+
+
+def run_etch(args, rank, world, local_rank):
+    from etch_b200 import _lib, build, sharding, synth
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl etch needs a CUDA device (there is no CPU fallback); use gpurun")
+    build.build()
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    B, N = args.batch, args.points
+    pipe = Pipeline(device)
+    n_pool = 4
+    host = [torch.from_numpy(synth.sample_scans(B, N, 50 + rank * 100 + i)).pin_memory() for i in range(n_pool)]
+    dev_in = [h.to(device) for h in host]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        pipe.step(dev_in[i % n_pool])
+    barrier()
+    # ---- timed region: device-resident inputs, L2 flushed between steps (flush not timed) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = _lib.launch_count
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        pipe.step(dev_in[i % n_pool])
+        ev[i][1].record()
+    barrier()
+    launches = (_lib.launch_count - l0)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([float(sum(step_ms))], device=device)
+    sharding.max_over_ranks(total_ms)
+    ms_per_step = total_ms.item() / args.steps
+    # ---- end to end: pinned host scans in, fitted mesh + parameters out, copies inside the timed region ----
+    out_v = torch.empty(B, 6890, 3, dtype=torch.float32).pin_memory()
+    out_p = torch.empty(B, 85, dtype=torch.float32).pin_memory()
+    out_j = torch.empty(B, 45, 3, dtype=torch.float32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        pts = host[i % n_pool].to(device, non_blocking=True)
+        fit = pipe.step(pts)
+        out_v.copy_(fit["vertices"], non_blocking=True)
+        out_p.copy_(fit["params"], non_blocking=True)
+        out_j.copy_(fit["joints"], non_blocking=True)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    sharding.max_over_ranks(e2e_ms)
+    e2e_ms_step = e2e_ms.item() / args.steps
+    # ---- instrumented step: per-kernel CUDA-event times on the launching stream ----
+    prof = None
+    if rank == 0:
+        _lib.start_profile()
+        pipe.step(dev_in[0])
+        prof = _lib.stop_profile()
+    barrier()
+    if rank != 0:
+        return
+    peaks = _peaks()
+    total_kernel_ms = sum(t for _, t in prof.values())
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    dom, (dom_calls, dom_ms) = top[0]
+    scale = N / 5000.0
+    algo = ALGO_GFLOP_5K.get(dom)
+    roofline = {"kernel": "etch_" + dom, "share_of_step": dom_ms / total_kernel_ms, "launches_per_step": dom_calls,
+                "avg_launch_ms": dom_ms / dom_calls, "traffic": None}
+    if algo is not None:
+        flops = algo * 1e9 * scale * B  # all launches of this kernel in one step
+        ach = flops / (dom_ms * 1e-3) / 1e12
+        roofline.update(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s", frac=ach / peaks["tensor"],
+                        peak_source="%s bf16 dense (MEASURED_PEAKS.json burst)" % peaks["which"],
+                        note="fp32 CUDA-core kernel this round (FP32 SIMT ceiling ~72 TFLOP/s); algorithmic flops = SURVEY 8d figure x scans")
+    else:
+        roofline.update(bound="latency", achieved=None, peak=None, unit=None, frac=None)
+    kernels = {k: {"calls": c, "ms": round(t, 4)} for k, (c, t) in top}
+    # ---- CPU baseline: the oracle port on the host cores, one scan (bounded sample) ----
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from etch_b200 import smpl_model
+        from etch_b200.models import spec
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = synth.make_state_dict(1)
+        body_t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in smpl_model.synthetic_body(0).items()}
+        t0 = time.time()
+        _oracle_scan_step(torch.from_numpy(synth.sample_scans(1, N, 100)), sd, spec.so3_tables(), body_t, list(pipe.ms.values()), len(pipe.ms))
+        dt = time.time() - t0
+        cpu_baseline = {"value": 1.0 / dt, "unit": "scans/s", "cores": cores, "kind": "port",
+                        "sample": "1 scan of %d points (net forward + 2-stage LM fit), %.1f s, torch-CPU/C oracle, untimed warm-up none" % (N, dt)}
+    scans = B * world
+    line = {"metric": "scans/sec (net fwd + SMPL fit)", "value": scans / (ms_per_step * 1e-3), "unit": "scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "5k-pt clothed scans, batch 8 per GPU, full net forward + 2-stage LM SMPL fit (BASELINE configs[1])",
+                       "points": N, "batch_per_gpu": B, "global_batch": scans, "parallelism": "scan-sharded x%d (no data-path collective)" % world,
+                       "weights": "seeded random init, reference state-dict layout", "body_model": "synthetic SMPL-shaped (6890 verts)",
+                       "l2": "256 MiB flush write between timed steps (not timed)"},
+            "e2e": {"value": scans / (e2e_ms_step * 1e-3), "unit": "scans/s", "ms_per_step": e2e_ms_step,
+                    "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": B * (6890 * 3 + 85 + 45 * 3) * 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels_ms": kernels}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="etch", choices=["etch", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--points", type=int, default=5000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_etch(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

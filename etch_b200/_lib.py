@@ -40,11 +40,40 @@ def f32(x):
     return ctypes.c_float(float(x))
 
 
+# kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim); everything not listed launches once
+_LAUNCHES_PER_CALL = {"lbs_forward": 2}
+launch_count = 0
+_profile = None  # when a dict: name -> [(start_event, end_event), ...]
+
+
+def start_profile():
+    global _profile
+    _profile = {}
+
+
+def stop_profile():
+    """-> {name: (calls, total_ms)} measured with CUDA events on the launching stream."""
+    global _profile
+    torch.cuda.synchronize()
+    out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in _profile.items()}
+    _profile = None
+    return out
+
+
 def call(name, *args):
     """Invoke ``int etch_<name>(..., cudaStream_t)`` on the current torch stream; raise on a non-zero status."""
+    global launch_count
     fn = getattr(lib(), "etch_" + name)
     fn.restype = ctypes.c_int
-    rc = fn(*args, stream())
+    launch_count += _LAUNCHES_PER_CALL.get(name, 1)
+    if _profile is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args, stream())
+        b.record()
+        _profile.setdefault(name, []).append((a, b))
+    else:
+        rc = fn(*args, stream())
     if rc != 0:
         raise RuntimeError("etch_b200: etch_%s failed with status %d (%s)" % (
             name, rc, "invalid argument" if rc == -1 else "unsupported" if rc == -2 else "cudaError"))
