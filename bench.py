@@ -96,16 +96,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def _oracle_scan_step(pts, sd, tables, body_t, vids, n_markers):
-    """one scan through the CPU oracle: network forward + post-processing + markers + 2-stage LM + final LBS."""
+LM_SAMPLE_ITERS = (3, 3)  # CPU sample: 3+3 of the 30+50 LM iterations, cost extrapolated linearly (every iteration costs the same)
+
+
+def _oracle_scan_seconds(pts, sd, tables, body_t, vids, n_markers):
+    """CPU seconds for ONE scan through the oracle port: full network forward + post-processing + markers, plus a
+    bounded sample of the 2-stage LM (LM_SAMPLE_ITERS iterations, scaled to the full 30+50) and the final LBS."""
     from oracle import lm as olm
     from oracle import net as onet
+    t0 = time.time()
     with torch.no_grad():
         out = onet.forward(pts, sd, tables)
         labels, vec, inner = onet.postprocess(pts, out)
         mk, valid = olm.get_markers(inner, labels, out["confidences"], n_markers)
-    fit = olm.fit(body_t, vids, mk, valid)
-    return fit["vertices"]
+    t_net = time.time() - t0
+    t0 = time.time()
+    olm.fit(body_t, vids, mk, valid, steps0=LM_SAMPLE_ITERS[0], steps1=LM_SAMPLE_ITERS[1])
+    t_lm = (time.time() - t0) * (30 + 50) / float(sum(LM_SAMPLE_ITERS))
+    return t_net + t_lm, t_net, t_lm
+
+
+def _cpu_threads():
+    # the torch-CPU oracle stops scaling (and degrades) beyond a few dozen threads on its small per-op tensors
+    return min(os.cpu_count() or 1, int(os.environ.get("ETCH_CPU_THREADS", "32")))
 
 
 def run_reference(args, rank, world):
@@ -117,7 +130,7 @@ def run_reference(args, rank, world):
     from etch_b200.models import spec
     from oracle import index_ops
     index_ops.lib()
-    cores = os.cpu_count() or 1
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     sd = synth.make_state_dict(1)
     tables = spec.so3_tables()
@@ -131,16 +144,17 @@ def run_reference(args, rank, world):
     warm = min(args.warmup, 1)
     for i in range(warm + args.steps):
         pts = torch.from_numpy(synth.sample_scans(1, args.points, 100 + i))
-        t0 = time.time()
-        _oracle_scan_step(pts, sd, tables, body_t, vids, len(ms))
-        dt = time.time() - t0
+        wall0 = time.time()
+        dt, _, _ = _oracle_scan_seconds(pts, sd, tables, body_t, vids, len(ms))
+        wall = time.time() - wall0
         if i >= warm:
             times.append(dt)
-        if time.time() - t_start + dt > budget_s and len(times) >= 1:
+        if time.time() - t_start + wall > budget_s and len(times) >= 1:
             break
     ms_step = 1000.0 * float(np.mean(times))
     value = 1000.0 / ms_step  # one scan per step
-    sample = "1 scan of %d points per step (net forward + 2-stage LM fit + final LBS), %d timed steps" % (args.points, len(times))
+    sample = ("1 scan of %d points per step: full net forward + markers, LM timed for %d+%d of 30+50 iterations and scaled "
+              "linearly; %d timed steps, %d torch threads" % (args.points, LM_SAMPLE_ITERS[0], LM_SAMPLE_ITERS[1], len(times), cores))
     line = {"impl": "reference", "metric": "scans/sec (net fwd + SMPL fit)", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -270,15 +284,15 @@ def run_etch(args, rank, world, local_rank):
     if not args.no_cpu_baseline:
         from etch_b200 import smpl_model
         from etch_b200.models import spec
-        cores = os.cpu_count() or 1
+        cores = _cpu_threads()
         torch.set_num_threads(cores)
         sd = synth.make_state_dict(1)
         body_t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in smpl_model.synthetic_body(0).items()}
-        t0 = time.time()
-        _oracle_scan_step(torch.from_numpy(synth.sample_scans(1, N, 100)), sd, spec.so3_tables(), body_t, list(pipe.ms.values()), len(pipe.ms))
-        dt = time.time() - t0
+        dt, t_net, t_lm = _oracle_scan_seconds(torch.from_numpy(synth.sample_scans(1, N, 100)), sd, spec.so3_tables(), body_t,
+                                               list(pipe.ms.values()), len(pipe.ms))
         cpu_baseline = {"value": 1.0 / dt, "unit": "scans/s", "cores": cores, "kind": "port",
-                        "sample": "1 scan of %d points (net forward + 2-stage LM fit), %.1f s, torch-CPU/C oracle, untimed warm-up none" % (N, dt)}
+                        "sample": "1 scan of %d points: net forward %.1f s + LM %.1f s (timed %d+%d of 30+50 iterations, scaled); "
+                                  "torch-CPU/C oracle, %d threads" % (N, t_net, t_lm, LM_SAMPLE_ITERS[0], LM_SAMPLE_ITERS[1], cores)}
     scans = B * world
     line = {"metric": "scans/sec (net fwd + SMPL fit)", "value": scans / (ms_per_step * 1e-3), "unit": "scans/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -126,12 +126,13 @@ __device__ void rodrigues_with_grad(const float* r, float* R, float* dR /*[3][9]
 }
 
 struct LmSmem {
-    float J[3 * NM_MAX * LDJ];        // residual Jacobian (rows = 3M)
-    float A[LDJ * LDA];               // J^T J + lambda I  -> Cholesky factor
+    float J[3 * NM_MAX * LDJ];        // residual Jacobian (rows = 3M); during lm_eval it holds the raw pose-blend terms q
+    float A[LDJ * LDA];               // [J^T J + lambda I ; -J^T r] (row D = right-hand side) -> Cholesky factor / y
     float cmk[NM_MAX * NJ * 3];       // marker transformed by bone k alone
     float S[NM_MAX * NJ * 3];         // sum over descendants of j of w (c_mk - t_j)
     float Tv[NM_MAX * 9];             // blended rotation per marker
     float vp[NM_MAX * 3];             // posed-template marker (before skinning)
+    float vpb[NM_MAX * 3];            // pose-blend offsets
     float res[NM_MAX * 3];            // residual
     float tgt[NM_MAX * 3];
     float mask[NM_MAX];
@@ -139,14 +140,15 @@ struct LmSmem {
     float dT[NJ * 30];                // d(posed joint k)/d beta_l
     float pf[207];
     float x[DMAX + 3];                // theta[72] | beta[10] | transl[3]
-    float g[LDJ];                     // J^T r  -> solution delta
+    float g[LDJ];                     // solution delta
     float red[32];
     float err;
 };
 
-// forward pass at the current parameters: kinematics, marker vertices, residual, error
+// forward pass at the current parameters: kinematics, marker vertices, residual, error.  The single sweep over the
+// marker rows of posedirs also leaves q[o][j*3+i] = sum_e dR_{j,i}[e] * P[(j-1)*9+e][o] in S.J for lm_jacobian.
 __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
-    const int tid = threadIdx.x, M = Bm.M;
+    const int tid = threadIdx.x, M = Bm.M, M3 = Bm.M * 3;
     float* theta = S.x; float* beta = S.x + 72; float* transl = S.x + 82;
     if (tid < NJ) {
         rodrigues_with_grad(theta + tid * 3, S.R + tid * 9, S.dR + tid * 27);
@@ -158,16 +160,15 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
         for (int l = 0; l < 10; ++l) v = fmaf(__ldg(Bm.Js + o * 10 + l), beta[l], v);
         S.Jr[o] = v;
     }
+    for (int o = tid; o < M3; o += blockDim.x) S.vpb[o] = 0.f;
     __syncthreads();
     if (tid < 32) {  // kinematic chain, one warp, 12 lanes = entries of [R|t]
         const int r = tid / 4, c = tid % 4;
         for (int j = 0; j < NJ; ++j) {
             if (tid < 12) {
                 const int pa = __ldg(Bm.parents + j);
-                float lv;  // local transform entry L[r'][c] needed below is read from R / rel joints
                 if (j == 0) {
-                    lv = c < 3 ? S.R[r * 3 + c] : S.Jr[r];
-                    S.G[r * 4 + c] = lv;
+                    S.G[r * 4 + c] = c < 3 ? S.R[r * 3 + c] : S.Jr[r];
                 } else {
                     const float* Gp = S.G + pa * 12;
                     float v = c == 3 ? Gp[r * 4 + 3] : 0.f;
@@ -180,13 +181,30 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
             }
             __syncwarp();
         }
-    } else {  // posed-template markers: v_p = T + S beta + P^T pose_feature
-        for (int o = tid - 32; o < M * 3; o += blockDim.x - 32) {
-            float v = __ldg(Bm.Tm + o);
-            for (int l = 0; l < 10; ++l) v = fmaf(__ldg(Bm.Sm + o * 10 + l), beta[l], v);
+    }
+    // fused pose-blend sweep: task = (output o, group of joints); each posedirs value feeds the blend and 3 Jacobian terms
+    {
+        const int nthr = blockDim.x - 32;
+        for (int t = tid - 32; t >= 0 && t < M3 * 4; t += nthr) {
+            const int o = t % M3, jg = t / M3;
+            const int j0 = 1 + jg * 6, j1 = min(NJ, j0 + 6);
             float acc = 0.f;
-            for (int k = 0; k < 207; ++k) acc = fmaf(S.pf[k], __ldg(Bm.Pm + (size_t)k * M * 3 + o), acc);
-            S.vp[o] = v + acc;
+            for (int j = j0; j < j1; ++j) {
+                float pv[9];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) pv[e] = __ldg(Bm.Pm + (size_t)((j - 1) * 9 + e) * M3 + o);
+                float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) {
+                    acc = fmaf(S.pf[(j - 1) * 9 + e], pv[e], acc);
+                    q0 = fmaf(S.dR[j * 27 + e], pv[e], q0);
+                    q1 = fmaf(S.dR[j * 27 + 9 + e], pv[e], q1);
+                    q2 = fmaf(S.dR[j * 27 + 18 + e], pv[e], q2);
+                }
+                S.J[o * LDJ + j * 3] = q0; S.J[o * LDJ + j * 3 + 1] = q1; S.J[o * LDJ + j * 3 + 2] = q2;
+            }
+            atomicAdd(&S.vpb[o], acc);
+            if (jg == 0) { S.J[o * LDJ] = 0.f; S.J[o * LDJ + 1] = 0.f; S.J[o * LDJ + 2] = 0.f; }
         }
     }
     __syncthreads();
@@ -194,6 +212,11 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
         const int j = tid / 3, c = tid % 3;
         const float* G = S.G + j * 12;
         S.ta[tid] = G[c * 4 + 3] - (G[c * 4] * S.Jr[j * 3] + G[c * 4 + 1] * S.Jr[j * 3 + 1] + G[c * 4 + 2] * S.Jr[j * 3 + 2]);
+    }
+    for (int o = tid; o < M3; o += blockDim.x) {
+        float v = __ldg(Bm.Tm + o);
+        for (int l = 0; l < 10; ++l) v = fmaf(__ldg(Bm.Sm + o * 10 + l), beta[l], v);
+        S.vp[o] = v + S.vpb[o];
     }
     __syncthreads();
     for (int t = tid; t < M * NJ; t += blockDim.x) {
@@ -210,7 +233,7 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
     }
     __syncthreads();
     float e2 = 0.f;
-    for (int o = tid; o < M * 3; o += blockDim.x) {
+    for (int o = tid; o < M3; o += blockDim.x) {
         const int m = o / 3, c = o % 3;
         float v = transl[c];
         for (int k = 0; k < NJ; ++k) v = fmaf(__ldg(Bm.Wm + m * NJ + k), S.cmk[(m * NJ + k) * 3 + c], v);
@@ -232,7 +255,6 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
 // analytic Jacobian of the residual at the state left by lm_eval; columns: theta(72) | beta(nb) | transl(3)
 __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
     const int tid = threadIdx.x, M = Bm.M;
-    const int D = 72 + nb + 3;
     // Omega_{j,i} = Rg_parent(j) dR_{j,i} Rg_j^T
     for (int t = tid; t < NJ * 3; t += blockDim.x) {
         const int j = t / 3;
@@ -256,7 +278,7 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
             }
     }
     // d(posed joint k)/d beta_l : chain over k for each (l, c)
-    for (int t = tid; t < nb * 3; t += blockDim.x) {
+    for (int t = tid - 96; t >= 0 && t < nb * 3; t += blockDim.x) {
         const int l = t / 3, c = t % 3;
         for (int k = 0; k < NJ; ++k) {
             const int pa = __ldg(Bm.parents + k);
@@ -287,7 +309,7 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
         S.S[t * 3] = sx; S.S[t * 3 + 1] = sy; S.S[t * 3 + 2] = sz;
     }
     __syncthreads();
-    // theta columns
+    // theta columns (in place: the raw q terms are replaced by the Jacobian entries)
     for (int t = tid; t < M * NJ * 3; t += blockDim.x) {
         const int m = t / (NJ * 3), ji = t % (NJ * 3), j = ji / 3;
         const float mk = S.mask[m];
@@ -297,15 +319,9 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
             const float* sv = S.S + (m * NJ + j) * 3;
             for (int c = 0; c < 3; ++c) d[c] = Om[c * 3] * sv[0] + Om[c * 3 + 1] * sv[1] + Om[c * 3 + 2] * sv[2];
             if (j >= 1) {
-                const float* dR = S.dR + ji * 9;
-                float q[3] = {0.f, 0.f, 0.f};
-                for (int e = 0; e < 9; ++e) {
-                    const float* prow = Bm.Pm + (size_t)((j - 1) * 9 + e) * M * 3 + m * 3;
-                    const float de = dR[e];
-                    q[0] = fmaf(de, __ldg(prow), q[0]); q[1] = fmaf(de, __ldg(prow + 1), q[1]); q[2] = fmaf(de, __ldg(prow + 2), q[2]);
-                }
+                const float q0 = S.J[(m * 3) * LDJ + ji], q1 = S.J[(m * 3 + 1) * LDJ + ji], q2 = S.J[(m * 3 + 2) * LDJ + ji];
                 const float* Tv = S.Tv + m * 9;
-                for (int c = 0; c < 3; ++c) d[c] += Tv[c * 3] * q[0] + Tv[c * 3 + 1] * q[1] + Tv[c * 3 + 2] * q[2];
+                for (int c = 0; c < 3; ++c) d[c] += Tv[c * 3] * q0 + Tv[c * 3 + 1] * q1 + Tv[c * 3 + 2] * q2;
             }
         }
         for (int c = 0; c < 3; ++c) S.J[(m * 3 + c) * LDJ + ji] = -mk * d[c];
@@ -334,67 +350,126 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
         const int m = t / 9, c = (t % 9) / 3, c2 = t % 3;
         S.J[(m * 3 + c) * LDJ + 72 + nb + c2] = c == c2 ? -S.mask[m] : 0.f;
     }
-    (void)D;
     __syncthreads();
 }
 
-// delta = (J^T J + lambda I)^-1 (-J^T r) by dense Cholesky; result in S.g[0..D)
+// delta = (J^T J + lambda I)^-1 (-J^T r): 4x4 register tiles for J^T J, blocked (4-column) right-looking Cholesky on the
+// matrix augmented with the right-hand side as an extra row (forward substitution comes for free), warp back-substitution.
 __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
     const int tid = threadIdx.x;
-    // A = J^T J (6x6 register tiles over the lower triangle incl. diagonal tiles)
-    const int nt = (D + 5) / 6;
-    for (int tile = tid; tile < nt * nt; tile += blockDim.x) {
-        const int ta = tile / nt, tb = tile % nt;
-        if (tb > ta) continue;
-        float acc[6][6];
-        for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+    const int nt = (D + 3) / 4;
+    for (int tile = tid; tile < nt * (nt + 1) / 2; tile += blockDim.x) {
+        int ta = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+        while ((ta + 1) * (ta + 2) / 2 <= tile) ++ta;
+        while (ta * (ta + 1) / 2 > tile) --ta;
+        const int tb = tile - ta * (ta + 1) / 2;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
         for (int r = 0; r < rows; ++r) {
-            const float* row = S.J + r * LDJ;
-            float a[6], b[6];
-            for (int i = 0; i < 6; ++i) { a[i] = ta * 6 + i < D ? row[ta * 6 + i] : 0.f; b[i] = tb * 6 + i < D ? row[tb * 6 + i] : 0.f; }
-            for (int i = 0; i < 6; ++i)
-                for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            const float4 a = *reinterpret_cast<const float4*>(S.J + r * LDJ + ta * 4);
+            const float4 b = *reinterpret_cast<const float4*>(S.J + r * LDJ + tb * 4);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) {
-                const int ia = ta * 6 + i, ib = tb * 6 + j;
-                if (ia < D && ib < D) {
-                    const float v = acc[i][j] + (ia == ib ? lambda : 0.f);
-                    S.A[ia * LDA + ib] = v;
-                    S.A[ib * LDA + ia] = v;
-                }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ia = ta * 4 + i, ib = tb * 4 + j;
+                if (ia < D && ib < D && ib <= ia) S.A[ia * LDA + ib] = acc[i][j] + (ia == ib ? lambda : 0.f);
             }
     }
-    for (int a = tid; a < D; a += blockDim.x) {
+    for (int a = tid; a < D; a += blockDim.x) {  // right-hand side as row D of the augmented matrix
         float v = 0.f;
         for (int r = 0; r < rows; ++r) v = fmaf(S.J[r * LDJ + a], S.res[r], v);
-        S.g[a] = -v;
+        S.A[D * LDA + a] = -v;
     }
     __syncthreads();
-    // Cholesky A = L L^T (right-looking, lower triangle in place)
-    for (int k = 0; k < D; ++k) {
-        if (tid == 0) S.A[k * LDA + k] = sqrtf(S.A[k * LDA + k]);
+    // blocked Cholesky, lower triangle in place, rows 0..D (row D = rhs -> y = L^-1 b)
+    for (int k0 = 0; k0 < D; k0 += 4) {
+        const int kb = min(4, D - k0);
+        // panel: every row i >= k0 solves its kb entries against the (redundantly factored) diagonal block
+        {
+            const int i = k0 + tid;
+            const bool act = i <= D;
+            float Ld[4][4], row[4];
+            if (act) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) Ld[a][b] = (a < kb && b <= a) ? S.A[(k0 + a) * LDA + k0 + b] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) row[c] = (c < kb && i >= k0 + kb) ? S.A[i * LDA + k0 + c] : 0.f;
+            }
+            __syncthreads();  // everybody has read the un-factored diagonal block before its owners overwrite it
+            if (act) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < kb) {
+                        float d = Ld[c][c];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) if (e < c) d = fmaf(-Ld[c][e], Ld[c][e], d);
+                        d = sqrtf(d);
+                        Ld[c][c] = d;
+                        const float inv = 1.0f / d;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r > c && r < kb) {
+                                float v = Ld[r][c];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (e < c) v = fmaf(-Ld[r][e], Ld[c][e], v);
+                                Ld[r][c] = v * inv;
+                            }
+                        }
+                    }
+                }
+                if (i < k0 + kb) {
+                    const int a = i - k0;
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa)
+                        if (aa == a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) if (b <= aa) S.A[i * LDA + k0 + b] = Ld[aa][b];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (c < kb) {
+                            float v = row[c];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) if (e < c) v = fmaf(-row[e], Ld[c][e], v);
+                            row[c] = v / Ld[c][c];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (c < kb) S.A[i * LDA + k0 + c] = row[c];
+                }
+            }
+        }
         __syncthreads();
-        const float inv = 1.0f / S.A[k * LDA + k];
-        for (int i = k + 1 + tid; i < D; i += blockDim.x) S.A[i * LDA + k] *= inv;
-        __syncthreads();
-        const int n = D - k - 1;
-        for (int t = tid; t < n * n; t += blockDim.x) {
-            const int i = k + 1 + t / n, j = k + 1 + t % n;
-            if (j <= i) S.A[i * LDA + j] = fmaf(-S.A[i * LDA + k], S.A[j * LDA + k], S.A[i * LDA + j]);
+        // trailing update: A[i][j] -= sum_c L[i][k0+c] L[j][k0+c] for k0+kb <= j <= i <= D (j < D)
+        const int n0 = k0 + kb;
+        const int nr = D + 1 - n0, nc = D - n0;
+        for (int t = tid; t < nr * nc; t += blockDim.x) {
+            const int i = n0 + t / nc, j = n0 + t % nc;
+            if (j <= i) {
+                float v = S.A[i * LDA + j];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (c < kb) v = fmaf(-S.A[i * LDA + k0 + c], S.A[j * LDA + k0 + c], v);
+                S.A[i * LDA + j] = v;
+            }
         }
         __syncthreads();
     }
-    // forward / backward substitution (one warp)
+    // backward substitution L^T x = y (y = row D), one warp
     if (tid < 32) {
-        for (int i = 0; i < D; ++i) {
-            float s = 0.f;
-            for (int k = tid; k < i; k += 32) s = fmaf(S.A[i * LDA + k], S.g[k], s);
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) S.g[i] = (S.g[i] - s) / S.A[i * LDA + i];
-            __syncwarp();
-        }
+        for (int i = tid; i < D; i += 32) S.g[i] = S.A[D * LDA + i];
+        __syncwarp();
         for (int i = D - 1; i >= 0; --i) {
             float s = 0.f;
             for (int k = i + 1 + tid; k < D; k += 32) s = fmaf(S.A[k * LDA + i], S.g[k], s);

@@ -1,0 +1,115 @@
+// tcgen05 (5th-gen tensor core) building blocks for sm_100a: TMEM allocation, shared-memory matrix descriptors,
+// kind::tf32 MMA issue with a 3xTF32 split (hi*hi + lo*hi + hi*lo keeps fp32-level accuracy), commit / mbarrier wait,
+// TMEM -> register loads.  Operand tiles use the canonical K-major NO-SWIZZLE layout
+//     element (r, k) of an [R x K] fp32 tile  ->  byte offset (k/4) * (R*16) + r*16 + (k%4)*4
+// i.e. core matrices (8 rows x 16 B) are contiguous over rows (SBO = 128 B) and R*16 B apart along K (LBO = R*16 B).
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle. lbo/sbo in bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// kind::tf32, D = f32, A and B K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// make generic-proxy shared-memory writes visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// one full warp; ncols power of two >= 32; the TMEM base address is written to *dst (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+// 32 lanes x 8 consecutive fp32 columns: thread i of the warp receives row (lane_base + i), columns [col, col+8)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 -> (hi, lo) with hi = round-to-nearest tf32, lo = x - hi (exact); the tensor core truncates lo to tf32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+// byte offset of element (r, k) in the canonical K-major no-swizzle tile with R rows
+__host__ __device__ __forceinline__ constexpr uint32_t tile_off(int r, int k, int R) {
+    return (uint32_t)((k >> 2) * (R * 16) + r * 16 + (k & 3) * 4);
+}
+
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T with the 3xTF32 split; issued by ONE thread.
+// a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses of canonical tiles ([128 x K] and [N x K]); K % 8 == 0.
+__device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                  int K, int N, bool accumulate_first) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16;
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t ah = make_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128), al = make_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
+        const uint64_t bh = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128), bl = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+        mma_tf32(tmem_d, ah, bh, idesc, (ks > 0 || accumulate_first) ? 1u : 0u);
+        mma_tf32(tmem_d, al, bh, idesc, 1u);
+        mma_tf32(tmem_d, ah, bl, idesc, 1u);
+    }
+}
+
+}  // namespace umma
