@@ -21,6 +21,7 @@ constexpr int NM_MAX = 96;     // markers supported by the shared-memory layout
 constexpr int DMAX = 85;       // 72 pose + 10 betas + 3 transl
 constexpr int LDJ = 88;        // padded leading dimension of J
 constexpr int LDA = 89;        // padded leading dimension of A = J^T J
+constexpr int TS = 5;          // tile size of the register-resident blocked Cholesky (85 = 17 x 5)
 
 // ------------------------------------------------------------------------------------------------ markers
 // one warp per (scan, label): top-3 confidences among the points carrying that label (ties: lower point index first)
@@ -142,6 +143,10 @@ struct LmSmem {
     float x[DMAX + 3];                // theta[72] | beta[10] | transl[3]
     float g[LDJ];                     // solution delta
     float red[32];
+    float Ld[TS * TS];                // current diagonal tile (un-factored) of the blocked Cholesky
+    float Lp[(DMAX / TS + 2) * TS * TS];  // factored column panel: one tile per block row (+ the rhs row)
+    float Wm[NM_MAX * NJ];            // skinning weights of the marker vertices
+    unsigned anc[NJ];
     float err;
 };
 
@@ -228,7 +233,7 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
     for (int t = tid; t < M * 9; t += blockDim.x) {
         const int m = t / 9, e = t % 9;
         float v = 0.f;
-        for (int k = 0; k < NJ; ++k) v = fmaf(__ldg(Bm.Wm + m * NJ + k), S.G[k * 12 + (e / 3) * 4 + (e % 3)], v);
+        for (int k = 0; k < NJ; ++k) v = fmaf(S.Wm[m * NJ + k], S.G[k * 12 + (e / 3) * 4 + (e % 3)], v);
         S.Tv[t] = v;
     }
     __syncthreads();
@@ -236,7 +241,7 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
     for (int o = tid; o < M3; o += blockDim.x) {
         const int m = o / 3, c = o % 3;
         float v = transl[c];
-        for (int k = 0; k < NJ; ++k) v = fmaf(__ldg(Bm.Wm + m * NJ + k), S.cmk[(m * NJ + k) * 3 + c], v);
+        for (int k = 0; k < NJ; ++k) v = fmaf(S.Wm[m * NJ + k], S.cmk[(m * NJ + k) * 3 + c], v);
         const float r = S.mask[m] * (S.tgt[o] - v);
         S.res[o] = r;
         e2 = fmaf(r, r, e2);
@@ -298,8 +303,8 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
         float sx = 0.f, sy = 0.f, sz = 0.f;
         const float tx = S.G[j * 12 + 3], ty = S.G[j * 12 + 7], tz = S.G[j * 12 + 11];
         for (int k = j; k < NJ; ++k) {
-            if ((__ldg(Bm.ancmask + k) >> j) & 1u) {
-                const float w = __ldg(Bm.Wm + m * NJ + k);
+            if ((S.anc[k] >> j) & 1u) {
+                const float w = S.Wm[m * NJ + k];
                 if (w != 0.f) {
                     const float* c = S.cmk + (m * NJ + k) * 3;
                     sx = fmaf(w, c[0] - tx, sx); sy = fmaf(w, c[1] - ty, sy); sz = fmaf(w, c[2] - tz, sz);
@@ -334,7 +339,7 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
         if (mk != 0.f) {
             const float s0 = __ldg(Bm.Sm + (m * 3 + 0) * 10 + l), s1 = __ldg(Bm.Sm + (m * 3 + 1) * 10 + l), s2 = __ldg(Bm.Sm + (m * 3 + 2) * 10 + l);
             for (int k = 0; k < NJ; ++k) {
-                const float w = __ldg(Bm.Wm + m * NJ + k);
+                const float w = S.Wm[m * NJ + k];
                 if (w == 0.f) continue;
                 const float a0 = s0 - __ldg(Bm.Js + (k * 3 + 0) * 10 + l), a1 = s1 - __ldg(Bm.Js + (k * 3 + 1) * 10 + l),
                             a2 = s2 - __ldg(Bm.Js + (k * 3 + 2) * 10 + l);
@@ -353,128 +358,173 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
     __syncthreads();
 }
 
-// delta = (J^T J + lambda I)^-1 (-J^T r): 4x4 register tiles for J^T J, blocked (4-column) right-looking Cholesky on the
-// matrix augmented with the right-hand side as an extra row (forward substitution comes for free), warp back-substitution.
+// delta = (J^T J + lambda I)^-1 (-J^T r).  The normal matrix never touches shared memory un-factored: thread t owns one
+// 5x5 tile of the lower triangle (plus 17 threads owning the 1x5 tiles of the right-hand side, appended as an extra block
+// row so that y = L^-1 b falls out of the factorisation), accumulates it from J in registers, and the right-looking
+// blocked Cholesky runs on those registers with two barriers per block column; a single warp then does the blocked
+// back-substitution L^T x = y.
 __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
     const int tid = threadIdx.x;
-    const int nt = (D + 3) / 4;
-    for (int tile = tid; tile < nt * (nt + 1) / 2; tile += blockDim.x) {
-        int ta = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
-        while ((ta + 1) * (ta + 2) / 2 <= tile) ++ta;
-        while (ta * (ta + 1) / 2 > tile) --ta;
-        const int tb = tile - ta * (ta + 1) / 2;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        for (int r = 0; r < rows; ++r) {
-            const float4 a = *reinterpret_cast<const float4*>(S.J + r * LDJ + ta * 4);
-            const float4 b = *reinterpret_cast<const float4*>(S.J + r * LDJ + tb * 4);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ia = ta * 4 + i, ib = tb * 4 + j;
-                if (ia < D && ib < D && ib <= ia) S.A[ia * LDA + ib] = acc[i][j] + (ia == ib ? lambda : 0.f);
-            }
+    const int NT = (D + TS - 1) / TS;
+    const int NTL = NT * (NT + 1) / 2;
+    int ta = -1, tb = -1;      // block row / column of my tile; ta == NT marks a right-hand-side tile
+    if (tid < NTL) {
+        ta = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+        while ((ta + 1) * (ta + 2) / 2 <= tid) ++ta;
+        while (ta * (ta + 1) / 2 > tid) --ta;
+        tb = tid - ta * (ta + 1) / 2;
+    } else if (tid < NTL + NT) {
+        ta = NT; tb = tid - NTL;
     }
-    for (int a = tid; a < D; a += blockDim.x) {  // right-hand side as row D of the augmented matrix
-        float v = 0.f;
-        for (int r = 0; r < rows; ++r) v = fmaf(S.J[r * LDJ + a], S.res[r], v);
-        S.A[D * LDA + a] = -v;
+    float acc[TS][TS];
+#pragma unroll
+    for (int i = 0; i < TS; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) acc[i][j] = 0.f;
+    if (ta >= 0 && ta < NT) {
+        for (int r = 0; r < rows; ++r) {
+            const float* row = S.J + r * LDJ;
+            float av[TS], bv[TS];
+#pragma unroll
+            for (int i = 0; i < TS; ++i) { av[i] = ta * TS + i < D ? row[ta * TS + i] : 0.f; bv[i] = tb * TS + i < D ? row[tb * TS + i] : 0.f; }
+#pragma unroll
+            for (int i = 0; i < TS; ++i)
+#pragma unroll
+                for (int j = 0; j < TS; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (ta == tb) {
+#pragma unroll
+            for (int i = 0; i < TS; ++i) acc[i][i] = ta * TS + i < D ? acc[i][i] + lambda : 1.0f;  // pad rows: identity
+        }
+    } else if (ta == NT) {
+        for (int r = 0; r < rows; ++r) {
+            const float rr = S.res[r];
+            const float* row = S.J + r * LDJ;
+#pragma unroll
+            for (int j = 0; j < TS; ++j) acc[0][j] = fmaf(tb * TS + j < D ? row[tb * TS + j] : 0.f, -rr, acc[0][j]);
+        }
+    }
+    for (int kb = 0; kb < NT; ++kb) {
+        if (ta == kb && tb == kb) {
+#pragma unroll
+            for (int i = 0; i < TS; ++i)
+#pragma unroll
+                for (int j = 0; j < TS; ++j) S.Ld[i * TS + j] = acc[i][j];
+        }
+        __syncthreads();
+        if (tb == kb && ta >= kb) {
+            float Lk[TS][TS];
+#pragma unroll
+            for (int i = 0; i < TS; ++i)
+#pragma unroll
+                for (int j = 0; j < TS; ++j) Lk[i][j] = j <= i ? S.Ld[i * TS + j] : 0.f;
+#pragma unroll
+            for (int c = 0; c < TS; ++c) {   // 5x5 Cholesky of the diagonal tile, redundantly in every panel thread
+                float d = Lk[c][c];
+#pragma unroll
+                for (int e = 0; e < TS; ++e) if (e < c) d = fmaf(-Lk[c][e], Lk[c][e], d);
+                d = sqrtf(d);
+                Lk[c][c] = d;
+                const float inv = 1.0f / d;
+#pragma unroll
+                for (int r = 0; r < TS; ++r) {
+                    if (r > c) {
+                        float v = Lk[r][c];
+#pragma unroll
+                        for (int e = 0; e < TS; ++e) if (e < c) v = fmaf(-Lk[r][e], Lk[c][e], v);
+                        Lk[r][c] = v * inv;
+                    }
+                }
+            }
+            if (ta == kb) {
+#pragma unroll
+                for (int i = 0; i < TS; ++i)
+#pragma unroll
+                    for (int j = 0; j < TS; ++j) acc[i][j] = Lk[i][j];
+            } else {   // X L_kk^T = A_ik  (row-wise forward substitution); rhs tiles only use row 0
+#pragma unroll
+                for (int i = 0; i < TS; ++i) {
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) {
+                        float v = acc[i][c];
+#pragma unroll
+                        for (int e = 0; e < TS; ++e) if (e < c) v = fmaf(-acc[i][e], Lk[c][e], v);
+                        acc[i][c] = v / Lk[c][c];
+                    }
+                }
+            }
+            float* lp = S.Lp + ta * TS * TS;
+#pragma unroll
+            for (int i = 0; i < TS; ++i)
+#pragma unroll
+                for (int j = 0; j < TS; ++j) {
+                    lp[i * TS + j] = acc[i][j];
+                    const int gi = ta * TS + i, gj = kb * TS + j;
+                    if (ta < NT) { if (gi < D && gj < D) S.A[gi * LDA + gj] = acc[i][j]; }
+                    else if (i == 0 && gj < D) S.A[D * LDA + gj] = acc[0][j];
+                }
+        }
+        __syncthreads();
+        if (tb > kb && ta >= tb) {   // trailing update A_ij -= L_ik L_jk^T
+            const float* li = S.Lp + ta * TS * TS;
+            const float* lj = S.Lp + tb * TS * TS;
+            float Lj[TS][TS];
+#pragma unroll
+            for (int j = 0; j < TS; ++j)
+#pragma unroll
+                for (int c = 0; c < TS; ++c) Lj[j][c] = lj[j * TS + c];
+            const int ni = ta == NT ? 1 : TS;
+#pragma unroll
+            for (int i = 0; i < TS; ++i) {
+                if (i < ni) {
+                    float Li[TS];
+#pragma unroll
+                    for (int c = 0; c < TS; ++c) Li[c] = li[i * TS + c];
+#pragma unroll
+                    for (int j = 0; j < TS; ++j)
+#pragma unroll
+                        for (int c = 0; c < TS; ++c) acc[i][j] = fmaf(-Li[c], Lj[j][c], acc[i][j]);
+                }
+            }
+        }
     }
     __syncthreads();
-    // blocked Cholesky, lower triangle in place, rows 0..D (row D = rhs -> y = L^-1 b)
-    for (int k0 = 0; k0 < D; k0 += 4) {
-        const int kb = min(4, D - k0);
-        // panel: every row i >= k0 solves its kb entries against the (redundantly factored) diagonal block
-        {
-            const int i = k0 + tid;
-            const bool act = i <= D;
-            float Ld[4][4], row[4];
-            if (act) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) Ld[a][b] = (a < kb && b <= a) ? S.A[(k0 + a) * LDA + k0 + b] : 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) row[c] = (c < kb && i >= k0 + kb) ? S.A[i * LDA + k0 + c] : 0.f;
-            }
-            __syncthreads();  // everybody has read the un-factored diagonal block before its owners overwrite it
-            if (act) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < kb) {
-                        float d = Ld[c][c];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) if (e < c) d = fmaf(-Ld[c][e], Ld[c][e], d);
-                        d = sqrtf(d);
-                        Ld[c][c] = d;
-                        const float inv = 1.0f / d;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (r > c && r < kb) {
-                                float v = Ld[r][c];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) if (e < c) v = fmaf(-Ld[r][e], Ld[c][e], v);
-                                Ld[r][c] = v * inv;
-                            }
-                        }
-                    }
-                }
-                if (i < k0 + kb) {
-                    const int a = i - k0;
-#pragma unroll
-                    for (int aa = 0; aa < 4; ++aa)
-                        if (aa == a)
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) if (b <= aa) S.A[i * LDA + k0 + b] = Ld[aa][b];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (c < kb) {
-                            float v = row[c];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) if (e < c) v = fmaf(-row[e], Ld[c][e], v);
-                            row[c] = v / Ld[c][c];
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) if (c < kb) S.A[i * LDA + k0 + c] = row[c];
-                }
-            }
-        }
-        __syncthreads();
-        // trailing update: A[i][j] -= sum_c L[i][k0+c] L[j][k0+c] for k0+kb <= j <= i <= D (j < D)
-        const int n0 = k0 + kb;
-        const int nr = D + 1 - n0, nc = D - n0;
-        for (int t = tid; t < nr * nc; t += blockDim.x) {
-            const int i = n0 + t / nc, j = n0 + t % nc;
-            if (j <= i) {
-                float v = S.A[i * LDA + j];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) if (c < kb) v = fmaf(-S.A[i * LDA + k0 + c], S.A[j * LDA + k0 + c], v);
-                S.A[i * LDA + j] = v;
-            }
-        }
-        __syncthreads();
-    }
-    // backward substitution L^T x = y (y = row D), one warp
+    // blocked back-substitution L^T x = y (y = row D of A), one warp; lane l accumulates the tiles of block rows kb+1+l, ...
     if (tid < 32) {
-        for (int i = tid; i < D; i += 32) S.g[i] = S.A[D * LDA + i];
+        for (int i = tid; i < NT * TS; i += 32) S.g[i] = i < D ? S.A[D * LDA + i] : 0.f;
         __syncwarp();
-        for (int i = D - 1; i >= 0; --i) {
-            float s = 0.f;
-            for (int k = i + 1 + tid; k < D; k += 32) s = fmaf(S.A[k * LDA + i], S.g[k], s);
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) S.g[i] = (S.g[i] - s) / S.A[i * LDA + i];
+        for (int kb = NT - 1; kb >= 0; --kb) {
+            float s[TS];
+#pragma unroll
+            for (int c = 0; c < TS; ++c) s[c] = 0.f;
+            for (int ib = kb + 1 + tid; ib < NT; ib += 32) {
+#pragma unroll
+                for (int r = 0; r < TS; ++r) {
+                    const int gi = ib * TS + r;
+                    if (gi < D) {
+                        const float xv = S.g[gi];
+#pragma unroll
+                        for (int c = 0; c < TS; ++c) { const int gc = kb * TS + c; if (gc < D) s[c] = fmaf(S.A[gi * LDA + gc], xv, s[c]); }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < TS; ++c)
+                for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+            if (tid == 0) {
+                float xk[TS];
+#pragma unroll
+                for (int c = TS - 1; c >= 0; --c) {
+                    const int gc = kb * TS + c;
+                    if (gc < D) {
+                        float v = S.g[gc] - s[c];
+#pragma unroll
+                        for (int e = TS - 1; e > c; --e) { const int ge = kb * TS + e; if (ge < D) v = fmaf(-S.A[ge * LDA + gc], xk[e], v); }
+                        xk[c] = v / S.A[gc * LDA + gc];
+                        S.g[gc] = xk[c];
+                    } else xk[c] = 0.f;
+                }
+            }
             __syncwarp();
         }
     }
@@ -491,6 +541,8 @@ __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict_
     for (int i = tid; i < DMAX + 3; i += blockDim.x) S.x[i] = 0.f;
     for (int i = tid; i < M * 3; i += blockDim.x) S.tgt[i] = __ldg(markers + (size_t)b * M * 3 + i);
     for (int i = tid; i < M; i += blockDim.x) S.mask[i] = valid[(size_t)b * M + i] ? 1.f : 0.f;
+    for (int i = tid; i < M * NJ; i += blockDim.x) S.Wm[i] = __ldg(Bm.Wm + i);
+    for (int i = tid; i < NJ; i += blockDim.x) S.anc[i] = __ldg(Bm.ancmask + i);
     __syncthreads();
     for (int stage = 0; stage < 2; ++stage) {
         const int nb = stage == 0 ? 2 : 10;

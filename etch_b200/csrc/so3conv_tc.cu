@@ -1,0 +1,219 @@
+// Tensor-core (tcgen05 + TMEM) versions of the dense-GEMM stages of the SO(3) encoder.
+//
+//   anchor_gemm_tc : IntraSO3Conv / skip 1x1 conv       z[(p,a), o] = sum_j sum_c x[p, tab[a][j], c] W_j[o, c] + bias[o]
+//   (same semantics as anchor_gemm_kernel in so3conv.cu; reference: vgtk/so3conv/functional.py:331-343, modules.py:19-39,
+//    131-153, src/models/so3conv.py:36-44,178-180)
+//
+// One CTA owns 2 points x 60 anchors = 120 GEMM rows padded to the UMMA M = 128.  For every anchor-neighbour slot j the
+// threads gather the (normalised) activation rows into the canonical K-major shared-memory tile, split fp32 -> (hi, lo)
+// TF32 pairs, and one thread issues hi*hi + lo*hi + hi*lo tcgen05.mma's that accumulate in TMEM (fp32-level accuracy).
+// The weight slices arrive pre-split and pre-tiled from the host through cp.async.bulk (TMA 1-D) on an mbarrier,
+// double-buffered so the copy of slice j+1 overlaps the MMAs of slice j.  Epilogue: tcgen05.ld -> bias -> shared tile ->
+// coalesced store + InstanceNorm statistics, as in the CUDA-core version.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int NA = 60;
+constexpr int TP = 2;
+constexpr int NPAIR = TP * NA;
+constexpr int MROWS = 128;
+
+__device__ __forceinline__ void stats_to_affine_tc(const double* sums, int b, int C, double count, float* s_mean, float* s_rstd) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double s = sums[((size_t)b * C + c) * 2], ss = sums[((size_t)b * C + c) * 2 + 1];
+        const double mean = s / count;
+        double var = ss / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[c] = (float)mean;
+        s_rstd[c] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+}
+
+using umma::bulk_load;
+
+template <int CIN, int COUT, int J, bool NORM_IN>
+__global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
+    const float* __restrict__ xin,       // [B,Q,60,CIN]
+    const int* __restrict__ src_idx,     // [B,P] or nullptr
+    const int* __restrict__ tab,         // [60][J]
+    const float* __restrict__ Wc,        // [J][2 (hi,lo)][CIN/4][COUT][4]  canonical K-major tiles, TF32-split on the host
+    const float* __restrict__ bias,      // [COUT]
+    const double* __restrict__ in_stats, double in_count, int Q, int P,
+    float* __restrict__ zraw, double* __restrict__ stats)
+{
+    constexpr int LD = CIN + 4;
+    constexpr uint32_t A_BYTES = MROWS * CIN * 4;     // one (hi or lo) A tile
+    constexpr uint32_t B_BYTES = COUT * CIN * 4;      // one (hi or lo) weight slice
+    constexpr int TCOLS = COUT < 32 ? 32 : COUT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* s_A = smem_raw;                                   // [hi | lo]
+    unsigned char* s_B = s_A + 2 * A_BYTES;                          // [2 buffers][hi | lo]
+    float* s_x = reinterpret_cast<float*>(s_B + 4 * B_BYTES);        // [120][LD]
+    float* s_mean = s_x + NPAIR * LD;
+    float* s_rstd = s_mean + CIN;
+    int* s_tab = reinterpret_cast<int*>(s_rstd + CIN);               // [60][J]
+    float* s_z = reinterpret_cast<float*>(s_A);                      // epilogue reuse [128][COUT]
+    __shared__ uint64_t bar_mma, bar_b[2];
+    __shared__ uint32_t tmem_base;
+
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < NA * J; i += 256) s_tab[i] = __ldg(tab + i);
+    if (NORM_IN) stats_to_affine_tc(in_stats, b, CIN, in_count, s_mean, s_rstd);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, TCOLS);
+    if (tid == 0) { umma::mbar_init(&bar_mma, 1); umma::mbar_init(&bar_b[0], 1); umma::mbar_init(&bar_b[1], 1); }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_base;
+    uint32_t n_mma = 0, n_b[2] = {0, 0};   // completed phases per barrier (uniform across threads)
+    double acc_s = 0.0, acc_ss = 0.0;
+    const int ntiles = (P + TP - 1) / TP;
+    // fill mapping: 2 threads per GEMM row, each half of the channels
+    const int frow = tid >> 1, fhalf = tid & 1;
+    const int fpair = frow < NPAIR ? frow : -1;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * TP;
+        const int npts = min(TP, P - p0);
+        // first weight slice of this tile (buffer 0 is free: every MMA of the previous tile has completed)
+        if (tid == 0) {
+            bulk_load(s_B, Wc, 2 * B_BYTES, &bar_b[0]);
+        }
+        // stage (and normalise) the activations of the tile's points; zero the pad rows of the A tiles
+        for (int t = tid; t < NPAIR * (CIN / 4); t += 256) {
+            const int row = t / (CIN / 4), c4 = t % (CIN / 4);
+            const int pl = row / NA;
+            const int p = min(p0 + pl, P - 1);
+            const int sp = src_idx ? __ldg(src_idx + (size_t)b * P + p) : p;
+            float4 v = __ldg(reinterpret_cast<const float4*>(xin + (((size_t)b * Q + sp) * NA + (row % NA)) * CIN) + c4);
+            if (NORM_IN) {
+                const int c = c4 * 4;
+                v.x = etch_lrelu((v.x - s_mean[c]) * s_rstd[c]);
+                v.y = etch_lrelu((v.y - s_mean[c + 1]) * s_rstd[c + 1]);
+                v.z = etch_lrelu((v.z - s_mean[c + 2]) * s_rstd[c + 2]);
+                v.w = etch_lrelu((v.w - s_mean[c + 3]) * s_rstd[c + 3]);
+            }
+            *reinterpret_cast<float4*>(s_x + row * LD + c4 * 4) = v;
+        }
+        for (int t = tid; t < (MROWS - NPAIR) * (CIN / 4) * 2; t += 256) {  // rows 120..127 of hi and lo stay zero
+            const int which = t / ((MROWS - NPAIR) * (CIN / 4)), rem = t % ((MROWS - NPAIR) * (CIN / 4));
+            const int r = NPAIR + rem / (CIN / 4), kc = rem % (CIN / 4);
+            *reinterpret_cast<float4*>(s_A + which * A_BYTES + kc * (MROWS * 16) + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        for (int j = 0; j < J; ++j) {
+            // gather + split the A tile for slot j
+            if (fpair >= 0) {
+                const int pl = fpair / NA, a = fpair % NA;
+                const float* xr = s_x + (pl * NA + s_tab[a * J + j]) * LD + fhalf * (CIN / 2);
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 8; ++c4) {
+                    const float4 v = *reinterpret_cast<const float4*>(xr + c4 * 4);
+                    float4 h, l;
+                    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+                    umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+                    const int kc = fhalf * (CIN / 8) + c4;
+                    *reinterpret_cast<float4*>(s_A + kc * (MROWS * 16) + frow * 16) = h;
+                    *reinterpret_cast<float4*>(s_A + A_BYTES + kc * (MROWS * 16) + frow * 16) = l;
+                }
+            }
+            umma::fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                const int buf = j & 1;
+                if (j + 1 < J) {  // prefetch the next slice into the other buffer (its last reader, MMA j-1, has completed)
+                    bulk_load(s_B + (buf ^ 1) * 2 * B_BYTES, Wc + (size_t)(j + 1) * 2 * COUT * CIN, 2 * B_BYTES, &bar_b[buf ^ 1]);
+                }
+                umma::mbar_wait(&bar_b[buf], n_b[buf] & 1);
+                umma::fence_after_sync();
+                const uint32_t a_hi = umma::smem_u32(s_A), a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
+                umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, CIN, COUT, j > 0);
+                umma::commit(&bar_mma);
+            }
+            n_b[j & 1]++;
+            // the A tile may only be overwritten once the MMAs reading it are done
+            umma::mbar_wait(&bar_mma, n_mma & 1);
+            n_mma++;
+            umma::fence_after_sync();
+        }
+        // ---- epilogue: TMEM -> registers -> (+bias) -> shared tile ----
+        {
+            const int q = warp & 3, half = warp >> 2;
+            const int row = q * 32 + (tid & 31);
+#pragma unroll
+            for (int c0 = 0; c0 < COUT / 2; c0 += 8) {
+                float v[8];
+                const int col = half * (COUT / 2) + c0;
+                umma::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + col, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s_z[row * COUT + col + i] = v[i] + __ldg(bias + col + i);
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        const int nvalid = npts * NA;
+        float* dst = zraw + ((size_t)b * P + p0) * NA * COUT;
+        for (int i = tid; i < nvalid * COUT / 4; i += 256)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_z)[i];
+        if (tid < COUT) {
+            float s = 0.f, ss = 0.f;
+            for (int r = 0; r < nvalid; ++r) { const float v = s_z[r * COUT + tid]; s += v; ss = fmaf(v, v, ss); }
+            acc_s += (double)s; acc_ss += (double)ss;
+        }
+        __syncthreads();  // s_z aliases the A tiles
+    }
+    if (tid < COUT) {
+        atomicAdd(stats + ((size_t)b * COUT + tid) * 2, acc_s);
+        atomicAdd(stats + ((size_t)b * COUT + tid) * 2 + 1, acc_ss);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+}
+
+int grid_for_tc(int ntiles, int B) {
+    int g = (148 + B - 1) / B;
+    return ntiles < g ? ntiles : g;
+}
+
+template <int CIN, int COUT, int J, bool NORM>
+int launch_agemm_tc(const float* xin, const int* src_idx, const int* tab, const float* Wc, const float* bias,
+                    const double* in_stats, double in_count, int B, int Q, int P, float* zraw, double* stats, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)2 * MROWS * CIN * 4 + (size_t)4 * COUT * CIN * 4 + (size_t)NPAIR * (CIN + 4) * 4 +
+                            (size_t)2 * CIN * 4 + (size_t)NA * J * 4 + 128;
+    static_assert((size_t)MROWS * COUT * 4 <= (size_t)2 * MROWS * CIN * 4, "epilogue tile must fit the A region");
+    auto kern = anchor_gemm_tc_kernel<CIN, COUT, J, NORM>;
+    ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(grid_for_tc((P + TP - 1) / TP, B), B);
+    kern<<<grid, 256, smem, stream>>>(xin, src_idx, tab, Wc, bias, in_stats, in_count, Q, P, zraw, stats);
+    ETCH_RETURN_LAST();
+}
+
+}  // namespace
+
+// Tensor-core IntraSO3Conv. Wc = [12][2][c/4][cout][4] (TF32 hi/lo split, canonical K-major tiles; see etch_b200/models/tc.py)
+ETCH_API int etch_so3_intra_conv_tc(const float* zin, const double* in_stats, const int* intra_idx, const float* Wc,
+                                    const float* bias, int B, int P, int c, int cout, float* zraw, double* stats,
+                                    cudaStream_t stream) {
+    if (!zin || !in_stats || !intra_idx || !Wc || !bias || !zraw || !stats) return ETCH_EINVAL;
+    const double cnt = (double)P * NA;
+    if (c == 32 && cout == 32) return launch_agemm_tc<32, 32, 12, true>(zin, nullptr, intra_idx, Wc, bias, in_stats, cnt, B, P, P, zraw, stats, stream);
+    if (c == 64 && cout == 64) return launch_agemm_tc<64, 64, 12, true>(zin, nullptr, intra_idx, Wc, bias, in_stats, cnt, B, P, P, zraw, stats, stream);
+    return ETCH_EINVAL;
+}
+
+// Tensor-core skip 1x1 conv. Wc = [1][2][cin/4][cout][4]
+ETCH_API int etch_so3_skip_conv_tc(const float* feat, const int* sample_idx, const int* ident, const float* Wc,
+                                   const float* bias, int B, int q, int P, int cin, int cout, float* zraw, double* stats,
+                                   cudaStream_t stream) {
+    if (!feat || !ident || !Wc || !bias || !zraw || !stats) return ETCH_EINVAL;
+    if (cin == 32 && cout == 32) return launch_agemm_tc<32, 32, 1, false>(feat, sample_idx, ident, Wc, bias, nullptr, 1.0, B, q, P, zraw, stats, stream);
+    if (cin == 32 && cout == 64) return launch_agemm_tc<32, 64, 1, false>(feat, sample_idx, ident, Wc, bias, nullptr, 1.0, B, q, P, zraw, stats, stream);
+    if (cin == 64 && cout == 64) return launch_agemm_tc<64, 64, 1, false>(feat, sample_idx, ident, Wc, bias, nullptr, 1.0, B, q, P, zraw, stats, stream);
+    return ETCH_EINVAL;
+}

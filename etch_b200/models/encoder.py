@@ -4,10 +4,16 @@ Only orchestration lives here: weight re-layout at load time, buffer allocation,
 Feature tensors are point-major ``[B, P, 60, C]`` (the reference keeps ``[B, C, P, 60]``); use ``to_reference_layout``
 when comparing.
 """
+import os
+
 import torch
 
 from .. import _lib as L
-from . import spec
+from . import spec, tc
+
+
+# tensor-core (tcgen05) kernels for the dense-GEMM stages; ETCH_B200_NO_TC=1 selects the fp32 CUDA-core versions (A/B tests)
+USE_TC = os.environ.get("ETCH_B200_NO_TC", "0") != "1"
 
 
 def to_reference_layout(feats_bpac):
@@ -42,6 +48,9 @@ class EncoderPlan:
                 b_intra=sd[pre + "intra_conv.conv.basic_conv.bias"].to(**f32).reshape(-1).contiguous(),
                 intra_idx=sd[pre + "intra_conv.conv.intra_idx"].to(device=device, dtype=torch.int32).contiguous(),
                 Wt_skip=sd[pre + "skip_conv.weight"].to(**f32).view(co, ci).t().contiguous(),  # [c][o]
+                # tensor-core operands: per anchor-neighbour slot j the [c_out x c] slice, TF32-split, canonical tiles
+                Wc_intra=torch.stack([tc.tc_operand(Wi.view(co, co, 12)[:, :, j].cpu(), "cpu") for j in range(12)], 0).contiguous().to(device),
+                Wc_skip=(tc.tc_operand(sd[pre + "skip_conv.weight"].view(co, ci).cpu(), device)[None].contiguous() if ci > 1 else None),
                 b_skip=sd[pre + "skip_conv.bias"].to(**f32).contiguous(),
             )
             self.layers.append(d)
@@ -79,8 +88,12 @@ def run_encoder(plan, xyz_bcn, trace=None):
                    L.ptr(lp["Wt_inter"]), L.ptr(lp["b_inter"]), B, q, P, nn_, ci, co, L.f32(lp["sigma"]), L.ptr(z1),
                    L.ptr(stats[0]))
         z2 = torch.empty_like(z1)
-        L.call("so3_intra_conv", L.ptr(z1), L.ptr(stats[0]), L.ptr(lp["intra_idx"]), L.ptr(lp["Wt_intra"]),
-               L.ptr(lp["b_intra"]), B, P, co, co, L.ptr(z2), L.ptr(stats[1]))
+        if USE_TC:
+            L.call("so3_intra_conv_tc", L.ptr(z1), L.ptr(stats[0]), L.ptr(lp["intra_idx"]), L.ptr(lp["Wc_intra"]),
+                   L.ptr(lp["b_intra"]), B, P, co, co, L.ptr(z2), L.ptr(stats[1]))
+        else:
+            L.call("so3_intra_conv", L.ptr(z1), L.ptr(stats[0]), L.ptr(lp["intra_idx"]), L.ptr(lp["Wt_intra"]),
+                   L.ptr(lp["b_intra"]), B, P, co, co, L.ptr(z2), L.ptr(stats[1]))
         out = torch.empty_like(z1)
         if ci == 1:
             # skip input is the constant occupancy feature: Conv1x1 gives a per-channel constant, whose InstanceNorm is 0
@@ -88,8 +101,8 @@ def run_encoder(plan, xyz_bcn, trace=None):
             L.call("so3_combine", L.ptr(z2), L.ptr(stats[1]), L.ptr(None), L.ptr(None), B, P, co, L.ptr(out))
         else:
             z3 = torch.empty_like(z1)
-            L.call("so3_skip_conv", L.ptr(feats), L.ptr(sidx), L.ptr(plan.ident), L.ptr(lp["Wt_skip"]), L.ptr(lp["b_skip"]),
-                   B, q, P, ci, co, L.ptr(z3), L.ptr(stats[2]))
+            L.call("so3_skip_conv_tc" if USE_TC else "so3_skip_conv", L.ptr(feats), L.ptr(sidx), L.ptr(plan.ident),
+                   L.ptr(lp["Wc_skip"] if USE_TC else lp["Wt_skip"]), L.ptr(lp["b_skip"]), B, q, P, ci, co, L.ptr(z3), L.ptr(stats[2]))
             L.call("so3_combine", L.ptr(z2), L.ptr(stats[1]), L.ptr(z3), L.ptr(stats[2]), B, P, co, L.ptr(out))
         if trace is not None:
             trace.append(dict(sample_idx=sidx, ball_idx=nbr, xyz=new_xyz, inter_z=z1, intra_z=z2, skip_z=z3, out=out))

@@ -6,13 +6,16 @@ Reference modules restated: src/models/direction_backbones.py:129-223, src/model
 src/models/models_pointcloud.py:94-126.
 """
 import math
+import os
 
 import torch
 
 from .. import _lib as L
+from . import tc
 from .spec import PT_BLOCKS, PT_NSAMPLE, PT_STRIDE
 
 EPS_BN = 1e-5
+USE_TC = os.environ.get("ETCH_B200_NO_TC", "0") != "1"  # tcgen05 kernels (default) vs fp32 CUDA-core versions
 
 
 # ----------------------------------------------------------------------------- direction head
@@ -134,7 +137,11 @@ class PTPlan:
         if prefix.startswith("confidence"):
             s, h = _fold_bn(sd, prefix + "cls.1.", d, sd[prefix + "cls.0.bias"])
             k = sd[prefix + "cls.3.weight"].shape[0]
-            self.head = dict(kind="conf", K=k, Wc0t=_wt(sd[prefix + "cls.0.weight"].squeeze(-1), d), sc=s, hc=h,
+            w0 = sd[prefix + "confi.0.weight"].squeeze(-1).float().cpu()  # [K*128, 128]
+            hi, lo = tc.split_tf32(w0)
+            tile = lambda t: t.view(k * 4, 32, 32, 4).permute(0, 2, 1, 3)  # noqa: E731  [chunk][k/4][n][4]
+            W0c = torch.stack([tile(hi), tile(lo)], 1).contiguous().to(device)
+            self.head = dict(kind="conf", K=k, W0c=W0c, Wc0t=_wt(sd[prefix + "cls.0.weight"].squeeze(-1), d), sc=s, hc=h,
                              Wc3t=_wt(sd[prefix + "cls.3.weight"].squeeze(-1), d), bc3=sd[prefix + "cls.3.bias"].to(**d).contiguous(),
                              W0t=_wt(sd[prefix + "confi.0.weight"].squeeze(-1), d), b0=sd[prefix + "confi.0.bias"].to(**d).contiguous(),
                              w2=sd[prefix + "confi.2.weight"].to(**d).reshape(k, -1).contiguous(),
@@ -250,8 +257,12 @@ def run_point_transformer(plan, geo, inv_feat_packed):
         hid = _linear(x1, h["Wc0t"], h["sc"], h["hc"], relu=True)
         logits = _linear(hid, h["Wc3t"], None, h["bc3"])
         conf = torch.empty(x1.shape[0], dtype=torch.float32, device=x1.device)
-        L.call("conf_head", L.ptr(x1), L.ptr(logits), L.ptr(h["W0t"]), L.ptr(h["b0"]), L.ptr(h["w2"]), L.ptr(h["b2"]),
-               x1.shape[0], h["K"], L.ptr(conf))
+        if USE_TC:
+            L.call("conf_head_tc", L.ptr(x1), L.ptr(logits), L.ptr(h["W0c"]), L.ptr(h["b0"]), L.ptr(h["w2"]), L.ptr(h["b2"]),
+                   x1.shape[0], h["K"], L.ptr(conf))
+        else:
+            L.call("conf_head", L.ptr(x1), L.ptr(logits), L.ptr(h["W0t"]), L.ptr(h["b0"]), L.ptr(h["w2"]), L.ptr(h["b2"]),
+                   x1.shape[0], h["K"], L.ptr(conf))
         return x1, logits, conf
     hid = _linear(x1, h["W0t"], h["s"], h["h"], relu=True)
     mag = _linear(hid, h["W3t"], None, h["b3"])
