@@ -151,3 +151,384 @@ ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float*
     conf_head_tc_kernel<<<grid, 256, smem, stream>>>(x, logits, W0c, b0, w2, b2, n, K, conf);
     ETCH_RETURN_LAST();
 }
+
+// =====================================================================================================================
+// Tensor-core direction head
+// =====================================================================================================================
+// Same math as direction_head_kernel (heads.cu): 3-NN blend of the coarse equivariant features -> 2 x MHSA over the 60
+// anchor tokens -> fused (head_combine o Linear1)+ReLU -> fused (Linear2 o so3_reg) -> chordal SO(3) mean -> direction.
+// Reference: src/models/models_pointcloud.py:111-126,181-184; direction_backbones.py:79-223; src/models/so3conv.py:186-225.
+//
+// One CTA = 2 points = 120 tokens (UMMA M = 128).  All projections run on tcgen05 (3xTF32, accumulators in TMEM):
+//   D[0:192]   = X  [Wq|Wk|Wv]^T      (Q stays in TMEM and is read per (token, head) with tcgen05.ld;
+//                                      K, V go to a token-major shared tile for the 60x60 attention)
+//   D[192:256] = O  Wc^T              (layer 1: + bias + residual -> X, re-split in place)
+//   D[256:384] = O  (W1 Wc2)^T        (layer 2 output folded with Linear1; ReLU and the 128->1 map are applied straight
+//                                      from TMEM, the hidden layer is never stored)
+// Activations live in shared memory as (hi, lo) TF32 pairs in the canonical UMMA layout (x == hi + lo exactly), weights
+// stream as 18 pre-split 32-row slices per tile through a 2-deep cp.async.bulk ring.  The softmax attention itself is
+// block-diagonal (60x60 per point and head) and stays on the CUDA cores.
+namespace {
+
+constexpr int DH_NA = 60;
+constexpr int DH_LDKV = 132;                       // floats per row of the K|V tile
+constexpr uint32_t DH_XB = 128 * 64 * 4;           // bytes of one canonical [128 x 64] tile
+constexpr uint32_t DH_WB = 32 * 64 * 4;            // bytes of one (hi or lo) weight slice [32 x 64]
+constexpr int DH_NCHUNK = 18;
+
+__device__ void dh_jacobi3(double A[3][3], double V[3][3], double e[3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+            }
+    }
+    e[0] = A[0][0]; e[1] = A[1][1]; e[2] = A[2][2];
+}
+
+// third column of U diag(1,1,det(UV^T)) V^T for Ce = U S V^T (see heads.cu::so3_direction)
+__device__ void dh_so3_direction(const double Ce[3][3], float out[3]) {
+    double A[3][3], V[3][3], e[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A[i][j] = Ce[0][i] * Ce[0][j] + Ce[1][i] * Ce[1][j] + Ce[2][i] * Ce[2][j];
+    dh_jacobi3(A, V, e);
+    int i0 = 0;
+    if (e[1] > e[i0]) i0 = 1;
+    if (e[2] > e[i0]) i0 = 2;
+    int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+    if (e[i2] > e[i1]) { const int t = i1; i1 = i2; i2 = t; }
+    const double v0[3] = {V[0][i0], V[1][i0], V[2][i0]}, v1[3] = {V[0][i1], V[1][i1], V[2][i1]};
+    double u0[3], u1[3];
+    for (int i = 0; i < 3; ++i) {
+        u0[i] = Ce[i][0] * v0[0] + Ce[i][1] * v0[1] + Ce[i][2] * v0[2];
+        u1[i] = Ce[i][0] * v1[0] + Ce[i][1] * v1[1] + Ce[i][2] * v1[2];
+    }
+    const double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]) + 1e-300;
+    for (int i = 0; i < 3; ++i) u0[i] /= n0;
+    const double d01 = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+    for (int i = 0; i < 3; ++i) u1[i] -= d01 * u0[i];
+    const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]) + 1e-300;
+    for (int i = 0; i < 3; ++i) u1[i] /= n1;
+    const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+    const double v2z = v0[0] * v1[1] - v0[1] * v1[0];
+    for (int i = 0; i < 3; ++i) out[i] = (float)(u0[i] * v0[2] + u1[i] * v1[2] + u2[i] * v2z);
+}
+
+struct DhIssuer {   // state of the single weight-streaming / MMA-issuing thread
+    const float* wall;      // [18][2][16][32][4]
+    unsigned char* s_B;     // [2][hi|lo]
+    uint64_t* b_full;
+    uint64_t* b_empty;
+    uint32_t gl, gm;        // global load / mma counters (ring phases run across tiles)
+    int ld;                 // slices loaded in the current tile
+    __device__ void load_next() {
+        if (ld >= DH_NCHUNK) return;
+        const uint32_t buf = gl & 1;
+        if (gl >= 2) umma::mbar_wait(&b_empty[buf], ((gl - 2) >> 1) & 1);
+        umma::bulk_load(s_B + buf * 2 * DH_WB, wall + (size_t)ld * 2 * 32 * 64, 2 * DH_WB, &b_full[buf]);
+        ++ld; ++gl;
+    }
+    __device__ void mma_slice(uint32_t a_hi, uint32_t a_lo, uint32_t tmem_d) {
+        const uint32_t buf = gm & 1;
+        umma::mbar_wait(&b_full[buf], (gm >> 1) & 1);
+        umma::fence_after_sync();
+        const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * DH_WB), b_lo = b_hi + DH_WB;
+        umma::issue_gemm_3xtf32(tmem_d, a_hi, a_lo, b_hi, b_lo, 64, 32, false);
+        umma::commit(&b_empty[buf]);
+        ++gm;
+        load_next();
+    }
+};
+
+// K (warps 0-3) / V (warps 4-7) columns of the QKV accumulator -> token-major shared tile
+__device__ __forceinline__ void dh_store_kv(uint32_t tmem, float* s_kv, int warp, int lane) {
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 64 + half * 64 + c0, v);
+        if (row < 2 * DH_NA) {
+            float* dst = s_kv + row * DH_LDKV + half * 64 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+    }
+}
+
+// softmax(q K^T) V for (token = my TMEM lane, my 4 heads); output written as (hi, lo) into the canonical O tile
+__device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, unsigned char* s_O, int warp, int lane) {
+    const int q = warp & 3, hq = (warp >> 2) * 4;
+    const int row = q * 32 + lane;
+    const bool valid = row < 2 * DH_NA;
+    const int base = (row >= DH_NA ? DH_NA : 0);
+    float qall[32];   // the whole warp loads its 4 heads' queries in one converged tcgen05.ld
+    umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + hq * 8, qall);
+    if (!valid) return;
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+        const int h = hq + hh;
+        float qv[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) qv[d] = qall[hh * 8 + d];
+        float s[DH_NA];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < DH_NA; ++j) {
+            const float* kr = s_kv + (base + j) * DH_LDKV + h * 8;
+            const float4 ka = *reinterpret_cast<const float4*>(kr);
+            const float4 kb = *reinterpret_cast<const float4*>(kr + 4);
+            float v = qv[0] * ka.x;
+            v = fmaf(qv[1], ka.y, v); v = fmaf(qv[2], ka.z, v); v = fmaf(qv[3], ka.w, v);
+            v = fmaf(qv[4], kb.x, v); v = fmaf(qv[5], kb.y, v); v = fmaf(qv[6], kb.z, v); v = fmaf(qv[7], kb.w, v);
+            s[j] = v;
+            mx = fmaxf(mx, v);
+        }
+        float sum = 0.f;
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < DH_NA; ++j) {
+            const float p = expf(s[j] - mx);
+            sum += p;
+            const float* vr = s_kv + (base + j) * DH_LDKV + 64 + h * 8;
+            const float4 va = *reinterpret_cast<const float4*>(vr);
+            const float4 vb = *reinterpret_cast<const float4*>(vr + 4);
+            o[0] = fmaf(p, va.x, o[0]); o[1] = fmaf(p, va.y, o[1]); o[2] = fmaf(p, va.z, o[2]); o[3] = fmaf(p, va.w, o[3]);
+            o[4] = fmaf(p, vb.x, o[4]); o[5] = fmaf(p, vb.y, o[5]); o[6] = fmaf(p, vb.z, o[6]); o[7] = fmaf(p, vb.w, o[7]);
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float4 hi, lo;
+            umma::split_tf32(o[g * 4 + 0] * inv, hi.x, lo.x); umma::split_tf32(o[g * 4 + 1] * inv, hi.y, lo.y);
+            umma::split_tf32(o[g * 4 + 2] * inv, hi.z, lo.z); umma::split_tf32(o[g * 4 + 3] * inv, hi.w, lo.w);
+            const int kc = h * 2 + g;
+            *reinterpret_cast<float4*>(s_O + kc * (128 * 16) + row * 16) = hi;
+            *reinterpret_cast<float4*>(s_O + DH_XB + kc * (128 * 16) + row * 16) = lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
+    const float* __restrict__ feats,   // [B,S,60,64]
+    const int* __restrict__ up_idx, const float* __restrict__ up_w,   // [B,N,3]
+    const float* __restrict__ wall,    // [18][2][16][32][4] weight slices
+    const float* __restrict__ bc1,     // [64]
+    const float* __restrict__ bf,      // [128]
+    const float* __restrict__ vreg,    // [128]
+    float creg, const float* __restrict__ anchors, int N, int S,
+    float* __restrict__ dir, float* __restrict__ anc_w)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* s_X = smem_raw;                         // [hi|lo] tokens
+    unsigned char* s_O = s_X + 2 * DH_XB;                  // [hi|lo] attention output
+    unsigned char* s_B = s_O + 2 * DH_XB;                  // [2][hi|lo] weight ring
+    float* s_kv = reinterpret_cast<float*>(s_B + 4 * DH_WB);   // [120][132]
+    float* s_part = s_kv + 2 * DH_NA * DH_LDKV;            // [2][128]
+    float* s_w = s_part + 256;                             // [128]
+    float* s_anc = s_w + 128;                              // [60][9]
+    __shared__ uint64_t b_full[2], b_empty[2], bar_mma;
+    __shared__ uint32_t tmem_base;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < DH_NA * 9; i += 256) s_anc[i] = __ldg(anchors + i);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
+    if (tid == 0) {
+        umma::mbar_init(&b_full[0], 1); umma::mbar_init(&b_full[1], 1);
+        umma::mbar_init(&b_empty[0], 1); umma::mbar_init(&b_empty[1], 1);
+        umma::mbar_init(&bar_mma, 1);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_base;
+    const uint32_t x_hi = umma::smem_u32(s_X), x_lo = x_hi + DH_XB, o_hi = umma::smem_u32(s_O), o_lo = o_hi + DH_XB;
+    DhIssuer iss{wall, s_B, b_full, b_empty, 0u, 0u, 0};
+    uint32_t n_mma = 0;
+    const int ntiles = (N + 1) / 2;
+    const float* F = feats + (size_t)b * S * DH_NA * 64;
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * 2;
+        if (tid == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
+        // ---- 0. blend the three coarse rows into the token tile (hi/lo, canonical) ----
+        {
+            const int r = tid >> 1, hf = tid & 1;
+            float4 acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < 2 * DH_NA) {
+                const int pl = r / DH_NA, a = r % DH_NA;
+                const int p = min(p0 + pl, N - 1);
+                const int* ip = up_idx + ((size_t)b * N + p) * 3;
+                const float* wp = up_w + ((size_t)b * N + p) * 3;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float wk = __ldg(wp + k);
+                    const float4* src = reinterpret_cast<const float4*>(F + ((size_t)__ldg(ip + k) * DH_NA + a) * 64 + hf * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 v = __ldg(src + i);
+                        acc[i].x = fmaf(v.x, wk, acc[i].x); acc[i].y = fmaf(v.y, wk, acc[i].y);
+                        acc[i].z = fmaf(v.z, wk, acc[i].z); acc[i].w = fmaf(v.w, wk, acc[i].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 hi, lo;
+                umma::split_tf32(acc[i].x, hi.x, lo.x); umma::split_tf32(acc[i].y, hi.y, lo.y);
+                umma::split_tf32(acc[i].z, hi.z, lo.z); umma::split_tf32(acc[i].w, hi.w, lo.w);
+                const int kc = hf * 8 + i;
+                *reinterpret_cast<float4*>(s_X + kc * (128 * 16) + r * 16) = hi;
+                *reinterpret_cast<float4*>(s_X + DH_XB + kc * (128 * 16) + r * 16) = lo;
+            }
+        }
+        for (int layer = 0; layer < 2; ++layer) {
+            umma::fence_async_smem();
+            __syncthreads();
+            // ---- QKV projection: 6 slices -> D[0:192] ----
+            if (tid == 0) {
+                umma::fence_after_sync();
+                for (int c = 0; c < 6; ++c) iss.mma_slice(x_hi, x_lo, tmem + c * 32);
+                umma::commit(&bar_mma);
+            }
+            umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
+            umma::fence_after_sync();
+            dh_store_kv(tmem, s_kv, warp, lane);
+            __syncthreads();
+            dh_attention(tmem, s_kv, s_O, warp, lane);
+            umma::fence_before_sync();
+            umma::fence_async_smem();
+            __syncthreads();
+            if (layer == 0) {
+                // ---- head_combine + bias + residual -> X ----
+                if (tid == 0) {
+                    umma::fence_after_sync();
+                    for (int c = 0; c < 2; ++c) iss.mma_slice(o_hi, o_lo, tmem + 192 + c * 32);
+                    umma::commit(&bar_mma);
+                }
+                umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
+                umma::fence_after_sync();
+                float v[32];
+                umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 192 + half * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int kc = (half * 32 + i) >> 2;
+                    float4* ph = reinterpret_cast<float4*>(s_X + kc * (128 * 16) + row * 16);
+                    float4* pl_ = reinterpret_cast<float4*>(s_X + DH_XB + kc * (128 * 16) + row * 16);
+                    const float4 xh = *ph, xl = *pl_;
+                    const int n0 = half * 32 + i;
+                    const float nx = (xh.x + xl.x) + (v[i] + __ldg(bc1 + n0)), ny = (xh.y + xl.y) + (v[i + 1] + __ldg(bc1 + n0 + 1));
+                    const float nz = (xh.z + xl.z) + (v[i + 2] + __ldg(bc1 + n0 + 2)), nw = (xh.w + xl.w) + (v[i + 3] + __ldg(bc1 + n0 + 3));
+                    float4 hi, lo;
+                    umma::split_tf32(nx, hi.x, lo.x); umma::split_tf32(ny, hi.y, lo.y);
+                    umma::split_tf32(nz, hi.z, lo.z); umma::split_tf32(nw, hi.w, lo.w);
+                    *ph = hi; *pl_ = lo;
+                }
+                umma::fence_before_sync();
+            }
+        }
+        // ---- fused (Linear1 o head_combine_2) + ReLU, then (so3_reg o Linear2): D[256:384] -> anchor weights ----
+        if (tid == 0) {
+            umma::fence_after_sync();
+            for (int c = 0; c < 4; ++c) iss.mma_slice(o_hi, o_lo, tmem + 256 + c * 32);
+            umma::commit(&bar_mma);
+        }
+        umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
+        umma::fence_after_sync();
+        {
+            float part = 0.f;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                float v[32];
+                umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + half * 64 + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n0 = half * 64 + c0 + i;
+                    part = fmaf(fmaxf(v[i] + __ldg(bf + n0), 0.f), __ldg(vreg + n0), part);
+                }
+            }
+            s_part[half * 128 + row] = part;
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid < 128) {
+            const float w = creg + s_part[tid] + s_part[128 + tid];
+            s_w[tid] = w;
+            if (anc_w && tid < 2 * DH_NA && p0 + tid / DH_NA < N) anc_w[((size_t)b * N + p0) * DH_NA + tid] = w;
+        }
+        __syncthreads();
+        if (tid < 2 && p0 + tid < N) {
+            double Ce[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int a = 0; a < DH_NA; ++a) {
+                const float wa = s_w[tid * DH_NA + a];
+                for (int e = 0; e < 9; ++e) Ce[e / 3][e % 3] += (double)(wa * s_anc[a * 9 + e]);
+            }
+            float d[3];
+            dh_so3_direction(Ce, d);
+            float* o = dir + ((size_t)b * N + p0 + tid) * 3;
+            o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
+        }
+        // the next tile's blend overwrites X only; s_w / s_part are rewritten after further barriers
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// inv[b,n,:] = sum_k w_k * mean_a feats[b, idx_k, a, :]   (anchor mean commutes with the 3-NN blend)
+__global__ void __launch_bounds__(256) anchor_mean_kernel(const float* __restrict__ feats, int total_pts, float* __restrict__ fmean) {
+    const int pt = blockIdx.x * 4 + (threadIdx.x >> 6), c = threadIdx.x & 63;
+    if (pt >= total_pts) return;
+    const float* p = feats + (size_t)pt * DH_NA * 64 + c;
+    float s = 0.f;
+#pragma unroll 4
+    for (int a = 0; a < DH_NA; ++a) s += __ldg(p + a * 64);
+    fmean[(size_t)pt * 64 + c] = s / 60.0f;
+}
+
+__global__ void __launch_bounds__(256) interp_inv_kernel(const float* __restrict__ fmean, const int* __restrict__ up_idx,
+                                                         const float* __restrict__ up_w, int N, int S, float* __restrict__ inv) {
+    const int b = blockIdx.y;
+    const int pt = blockIdx.x * 4 + (threadIdx.x >> 6), c = threadIdx.x & 63;
+    if (pt >= N) return;
+    const int* ip = up_idx + ((size_t)b * N + pt) * 3;
+    const float* wp = up_w + ((size_t)b * N + pt) * 3;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v = fmaf(__ldg(fmean + ((size_t)b * S + __ldg(ip + k)) * 64 + c), __ldg(wp + k), v);
+    inv[((size_t)b * N + pt) * 64 + c] = v;
+}
+
+}  // namespace
+
+// Tensor-core decode_direction. wall = the 18 weight slices [18][2][16][32][4] (see etch_b200/models/heads.py::DirectionPlan).
+// fmean_scratch [B,S,64] is caller-owned scratch for the per-coarse-point anchor mean.
+ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const float* up_w, const float* wall,
+                                    const float* bc1, const float* bf, const float* vreg, float creg, const float* anchors,
+                                    int B, int N, int S, float* dir, float* inv, float* anc_w, float* fmean_scratch,
+                                    cudaStream_t stream) {
+    if (!feats || !up_idx || !up_w || !wall || !bc1 || !bf || !vreg || !anchors || !dir || !inv || !fmean_scratch) return ETCH_EINVAL;
+    anchor_mean_kernel<<<etch_cdiv(B * S, 4), 256, 0, stream>>>(feats, B * S, fmean_scratch);
+    dim3 g2(etch_cdiv(N, 4), B);
+    interp_inv_kernel<<<g2, 256, 0, stream>>>(fmean_scratch, up_idx, up_w, N, S, inv);
+    const size_t smem = (size_t)4 * DH_XB + (size_t)4 * DH_WB + (size_t)(2 * DH_NA * DH_LDKV + 256 + 128 + DH_NA * 9) * 4 + 128;
+    ETCH_TRY(cudaFuncSetAttribute(direction_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (N + 1) / 2;
+    int gx = (148 + B - 1) / B;
+    if (gx > ntiles) gx = ntiles;
+    dim3 grid(gx, B);
+    direction_head_tc_kernel<<<grid, 256, smem, stream>>>(feats, up_idx, up_w, wall, bc1, bf, vreg, creg, anchors, N, S, dir, anc_w);
+    ETCH_RETURN_LAST();
+}

@@ -43,6 +43,16 @@ class DirectionPlan:
         self.vreg = (w2.t() @ wr).contiguous().to(**dev)          # [128]      so3_reg o Linear2
         self.creg = float(b2 @ wr + br[0])
         self.anchors = anchors.reshape(60, 9).contiguous().to(**dev)
+        # tensor-core operands: 18 slices of 32 output rows x 64 inputs, in consumption order
+        #   layer 0: Wq/sqrt(dk), Wk, Wv (2 slices each), head_combine (2); layer 1: Wq/sqrt(dk), Wk, Wv (6); Linear1 o head_combine (4)
+        def rows(layer):
+            pre = "direction_encoder.self_attention_layers.%d." % layer
+            wq, wk, wv = f64(pre + "query_transform.weight"), f64(pre + "key_transform.weight"), f64(pre + "value_transform.weight")
+            return [wq / math.sqrt(wq.shape[0] // 8), wk, wv]
+        mats = rows(0) + [f64("direction_encoder.self_attention_layers.0.head_combine.weight")] + rows(1) + [w1 @ wc2]
+        allrows = torch.cat(mats, 0).float()          # [576, 64]
+        assert allrows.shape == (576, 64)
+        self.wall = torch.stack([tc.tc_operand(allrows[i * 32:(i + 1) * 32], "cpu") for i in range(18)], 0).contiguous().to(device)
 
 
 def run_direction(plan, hitpts, xyz2_b3s, feats2, want_anchor_weights=False):
@@ -56,9 +66,14 @@ def run_direction(plan, hitpts, xyz2_b3s, feats2, want_anchor_weights=False):
     direction = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
     inv = torch.empty(B, N, 64, dtype=torch.float32, device=dev)
     anc_w = torch.empty(B, N, 60, dtype=torch.float32, device=dev) if want_anchor_weights else None
-    L.call("direction_head", L.ptr(feats2), L.ptr(up_idx), L.ptr(up_w), L.ptr(plan.Wqkv1), L.ptr(plan.Wc1), L.ptr(plan.bc1),
-           L.ptr(plan.Wqkv2), L.ptr(plan.Wf), L.ptr(plan.bf), L.ptr(plan.vreg), L.f32(plan.creg), L.ptr(plan.anchors),
-           B, N, S, L.ptr(direction), L.ptr(inv), L.ptr(anc_w))
+    if USE_TC:
+        fmean = torch.empty(B, S, 64, dtype=torch.float32, device=dev)
+        L.call("direction_head_tc", L.ptr(feats2), L.ptr(up_idx), L.ptr(up_w), L.ptr(plan.wall), L.ptr(plan.bc1), L.ptr(plan.bf),
+               L.ptr(plan.vreg), L.f32(plan.creg), L.ptr(plan.anchors), B, N, S, L.ptr(direction), L.ptr(inv), L.ptr(anc_w), L.ptr(fmean))
+    else:
+        L.call("direction_head", L.ptr(feats2), L.ptr(up_idx), L.ptr(up_w), L.ptr(plan.Wqkv1), L.ptr(plan.Wc1), L.ptr(plan.bc1),
+               L.ptr(plan.Wqkv2), L.ptr(plan.Wf), L.ptr(plan.bf), L.ptr(plan.vreg), L.f32(plan.creg), L.ptr(plan.anchors),
+               B, N, S, L.ptr(direction), L.ptr(inv), L.ptr(anc_w))
     return direction, inv, anc_w, up_idx, up_w
 
 
