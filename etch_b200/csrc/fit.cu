@@ -145,7 +145,10 @@ struct LmSmem {
     float red[32];
     float Ld[TS * TS];                // current diagonal tile (un-factored) of the blocked Cholesky
     float Lp[(DMAX / TS + 2) * TS * TS];  // factored column panel: one tile per block row (+ the rhs row)
-    float Wm[NM_MAX * NJ];            // skinning weights of the marker vertices
+    float Wm[NM_MAX * NJ];            // skinning weights of the marker vertices, COMPACTED: the nzc[m] non-zero ones first
+    unsigned char nzk[NM_MAX * NJ];   // bone index of the i-th non-zero weight of marker m
+    int nzc[NM_MAX];                  // number of non-zero weights of marker m
+    float dinv[LDJ];                  // reciprocal diagonal of the Cholesky factor
     unsigned anc[NJ];
     float err;
 };
@@ -224,16 +227,19 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
         S.vp[o] = v + S.vpb[o];
     }
     __syncthreads();
-    for (int t = tid; t < M * NJ; t += blockDim.x) {
-        const int m = t / NJ, k = t % NJ;
-        const float* G = S.G + k * 12;
-        const float x = S.vp[m * 3], y = S.vp[m * 3 + 1], z = S.vp[m * 3 + 2];
-        for (int c = 0; c < 3; ++c) S.cmk[t * 3 + c] = fmaf(G[c * 4], x, fmaf(G[c * 4 + 1], y, fmaf(G[c * 4 + 2], z, S.ta[k * 3 + c])));
+    for (int t = tid; t < M * NJ; t += blockDim.x) {   // entry i of marker m = its i-th non-zero bone
+        const int m = t / NJ, i = t % NJ;
+        if (i < S.nzc[m]) {
+            const int k = S.nzk[t];
+            const float* G = S.G + k * 12;
+            const float x = S.vp[m * 3], y = S.vp[m * 3 + 1], z = S.vp[m * 3 + 2];
+            for (int c = 0; c < 3; ++c) S.cmk[t * 3 + c] = fmaf(G[c * 4], x, fmaf(G[c * 4 + 1], y, fmaf(G[c * 4 + 2], z, S.ta[k * 3 + c])));
+        }
     }
     for (int t = tid; t < M * 9; t += blockDim.x) {
         const int m = t / 9, e = t % 9;
         float v = 0.f;
-        for (int k = 0; k < NJ; ++k) v = fmaf(S.Wm[m * NJ + k], S.G[k * 12 + (e / 3) * 4 + (e % 3)], v);
+        for (int i = 0; i < S.nzc[m]; ++i) v = fmaf(S.Wm[m * NJ + i], S.G[S.nzk[m * NJ + i] * 12 + (e / 3) * 4 + (e % 3)], v);
         S.Tv[t] = v;
     }
     __syncthreads();
@@ -241,7 +247,7 @@ __device__ void lm_eval(LmSmem& S, const BodyMarkers& Bm) {
     for (int o = tid; o < M3; o += blockDim.x) {
         const int m = o / 3, c = o % 3;
         float v = transl[c];
-        for (int k = 0; k < NJ; ++k) v = fmaf(S.Wm[m * NJ + k], S.cmk[(m * NJ + k) * 3 + c], v);
+        for (int i = 0; i < S.nzc[m]; ++i) v = fmaf(S.Wm[m * NJ + i], S.cmk[(m * NJ + i) * 3 + c], v);
         const float r = S.mask[m] * (S.tgt[o] - v);
         S.res[o] = r;
         e2 = fmaf(r, r, e2);
@@ -302,13 +308,12 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
         const int m = t / NJ, j = t % NJ;
         float sx = 0.f, sy = 0.f, sz = 0.f;
         const float tx = S.G[j * 12 + 3], ty = S.G[j * 12 + 7], tz = S.G[j * 12 + 11];
-        for (int k = j; k < NJ; ++k) {
+        for (int i = 0; i < S.nzc[m]; ++i) {
+            const int k = S.nzk[m * NJ + i];
             if ((S.anc[k] >> j) & 1u) {
-                const float w = S.Wm[m * NJ + k];
-                if (w != 0.f) {
-                    const float* c = S.cmk + (m * NJ + k) * 3;
-                    sx = fmaf(w, c[0] - tx, sx); sy = fmaf(w, c[1] - ty, sy); sz = fmaf(w, c[2] - tz, sz);
-                }
+                const float w = S.Wm[m * NJ + i];
+                const float* c = S.cmk + (m * NJ + i) * 3;
+                sx = fmaf(w, c[0] - tx, sx); sy = fmaf(w, c[1] - ty, sy); sz = fmaf(w, c[2] - tz, sz);
             }
         }
         S.S[t * 3] = sx; S.S[t * 3 + 1] = sy; S.S[t * 3 + 2] = sz;
@@ -338,9 +343,9 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
         float d[3] = {0.f, 0.f, 0.f};
         if (mk != 0.f) {
             const float s0 = __ldg(Bm.Sm + (m * 3 + 0) * 10 + l), s1 = __ldg(Bm.Sm + (m * 3 + 1) * 10 + l), s2 = __ldg(Bm.Sm + (m * 3 + 2) * 10 + l);
-            for (int k = 0; k < NJ; ++k) {
-                const float w = S.Wm[m * NJ + k];
-                if (w == 0.f) continue;
+            for (int i = 0; i < S.nzc[m]; ++i) {
+                const float w = S.Wm[m * NJ + i];
+                const int k = S.nzk[m * NJ + i];
                 const float a0 = s0 - __ldg(Bm.Js + (k * 3 + 0) * 10 + l), a1 = s1 - __ldg(Bm.Js + (k * 3 + 1) * 10 + l),
                             a2 = s2 - __ldg(Bm.Js + (k * 3 + 2) * 10 + l);
                 const float* G = S.G + k * 12;
@@ -418,14 +423,15 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
             for (int i = 0; i < TS; ++i)
 #pragma unroll
                 for (int j = 0; j < TS; ++j) Lk[i][j] = j <= i ? S.Ld[i * TS + j] : 0.f;
+            float dinv[TS];
 #pragma unroll
             for (int c = 0; c < TS; ++c) {   // 5x5 Cholesky of the diagonal tile, redundantly in every panel thread
                 float d = Lk[c][c];
 #pragma unroll
                 for (int e = 0; e < TS; ++e) if (e < c) d = fmaf(-Lk[c][e], Lk[c][e], d);
-                d = sqrtf(d);
-                Lk[c][c] = d;
-                const float inv = 1.0f / d;
+                const float inv = rsqrtf(d);
+                dinv[c] = inv;
+                Lk[c][c] = d * inv;
 #pragma unroll
                 for (int r = 0; r < TS; ++r) {
                     if (r > c) {
@@ -438,9 +444,11 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
             }
             if (ta == kb) {
 #pragma unroll
-                for (int i = 0; i < TS; ++i)
+                for (int i = 0; i < TS; ++i) {
 #pragma unroll
                     for (int j = 0; j < TS; ++j) acc[i][j] = Lk[i][j];
+                    if (kb * TS + i < D) S.dinv[kb * TS + i] = dinv[i];
+                }
             } else {   // X L_kk^T = A_ik  (row-wise forward substitution); rhs tiles only use row 0
 #pragma unroll
                 for (int i = 0; i < TS; ++i) {
@@ -449,7 +457,7 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
                         float v = acc[i][c];
 #pragma unroll
                         for (int e = 0; e < TS; ++e) if (e < c) v = fmaf(-acc[i][e], Lk[c][e], v);
-                        acc[i][c] = v / Lk[c][c];
+                        acc[i][c] = v * dinv[c];
                     }
                 }
             }
@@ -520,7 +528,7 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
                         float v = S.g[gc] - s[c];
 #pragma unroll
                         for (int e = TS - 1; e > c; --e) { const int ge = kb * TS + e; if (ge < D) v = fmaf(-S.A[ge * LDA + gc], xk[e], v); }
-                        xk[c] = v / S.A[gc * LDA + gc];
+                        xk[c] = v * S.dinv[gc];
                         S.g[gc] = xk[c];
                     } else xk[c] = 0.f;
                 }
@@ -534,14 +542,22 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
 __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict__ markers, const unsigned char* __restrict__ valid,
                                                         BodyMarkers Bm, int it0, int it1, float step0, float step1,
                                                         float damp0, float damp1, float* __restrict__ params,
-                                                        int* __restrict__ iters, float* __restrict__ errs) {
+                                                        int* __restrict__ iters, float* __restrict__ errs,
+                                                        long long* __restrict__ prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LmSmem& S = *reinterpret_cast<LmSmem*>(smem_raw);
     const int b = blockIdx.x, tid = threadIdx.x, M = Bm.M;
     for (int i = tid; i < DMAX + 3; i += blockDim.x) S.x[i] = 0.f;
     for (int i = tid; i < M * 3; i += blockDim.x) S.tgt[i] = __ldg(markers + (size_t)b * M * 3 + i);
     for (int i = tid; i < M; i += blockDim.x) S.mask[i] = valid[(size_t)b * M + i] ? 1.f : 0.f;
-    for (int i = tid; i < M * NJ; i += blockDim.x) S.Wm[i] = __ldg(Bm.Wm + i);
+    for (int m = tid; m < M; m += blockDim.x) {   // compact the (sparse: <= 4 non-zeros for SMPL) skinning weights
+        int cnt = 0;
+        for (int k = 0; k < NJ; ++k) {
+            const float w = __ldg(Bm.Wm + m * NJ + k);
+            if (w != 0.f) { S.Wm[m * NJ + cnt] = w; S.nzk[m * NJ + cnt] = (unsigned char)k; ++cnt; }
+        }
+        S.nzc[m] = cnt;
+    }
     for (int i = tid; i < NJ; i += blockDim.x) S.anc[i] = __ldg(Bm.ancmask + i);
     __syncthreads();
     for (int stage = 0; stage < 2; ++stage) {
@@ -552,16 +568,23 @@ __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict_
         lm_eval(S, Bm);
         float last = S.err;
         int done = 0;
+        long long t_eval = 0, t_jac = 0, t_solve = 0;
         for (int it = 0; it < maxit; ++it) {
+            long long c0 = clock64();
             lm_jacobian(S, Bm, nb);
+            long long c1 = clock64();
             lm_solve(S, M * 3, D, lambda);
+            long long c2 = clock64();
+            t_jac += c1 - c0; t_solve += c2 - c1;
             // x <- x + step * delta   (columns: theta | beta[0..nb) | transl)
             for (int a = tid; a < D; a += blockDim.x) {
                 const int xi = a < 72 ? a : (a < 72 + nb ? a : 82 + (a - 72 - nb));
                 S.x[xi] = fmaf(step, S.g[a], S.x[xi]);
             }
             __syncthreads();
+            c0 = clock64();
             lm_eval(S, Bm);
+            t_eval += clock64() - c0;
             const float err = S.err;
             done = it + 1;
             const float ae = fabsf(last - err);
@@ -569,7 +592,10 @@ __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict_
             if (conv) break;
             last = err;
         }
-        if (tid == 0) { iters[b * 2 + stage] = done; errs[b * 2 + stage] = S.err; }
+        if (tid == 0) {
+            iters[b * 2 + stage] = done; errs[b * 2 + stage] = S.err;
+            if (prof) { prof[(b * 2 + stage) * 3] = t_eval; prof[(b * 2 + stage) * 3 + 1] = t_jac; prof[(b * 2 + stage) * 3 + 2] = t_solve; }
+        }
         __syncthreads();
     }
     for (int i = tid; i < DMAX; i += blockDim.x) params[(size_t)b * DMAX + i] = S.x[i];
@@ -687,7 +713,20 @@ ETCH_API int etch_lm_fit(const float* markers, const unsigned char* valid, const
     BodyMarkers Bm{Tm, Sm, Pm, Wm, Jt, Js, parents, ancmask, M};
     const size_t smem = sizeof(LmSmem);
     ETCH_TRY(cudaFuncSetAttribute(lm_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lm_fit_kernel<<<B, 256, smem, stream>>>(markers, valid, Bm, steps0, steps1, step0, step1, damp0, damp1, params, iters, errs);
+    lm_fit_kernel<<<B, 256, smem, stream>>>(markers, valid, Bm, steps0, steps1, step0, step1, damp0, damp1, params, iters, errs, nullptr);
+    ETCH_RETURN_LAST();
+}
+
+// same solve, additionally returning SM-clock totals per (scan, stage): [eval, jacobian, solve]  (profiling aid for tools/)
+ETCH_API int etch_lm_fit_profile(const float* markers, const unsigned char* valid, const float* Tm, const float* Sm, const float* Pm,
+                                 const float* Wm, const float* Jt, const float* Js, const int* parents, const unsigned* ancmask,
+                                 int B, int M, int steps0, int steps1, float step0, float step1, float damp0, float damp1,
+                                 float* params, int* iters, float* errs, long long* prof, cudaStream_t stream) {
+    if (!markers || !valid || !params || !iters || !errs || !prof || B <= 0 || M <= 0 || M > NM_MAX) return ETCH_EINVAL;
+    BodyMarkers Bm{Tm, Sm, Pm, Wm, Jt, Js, parents, ancmask, M};
+    const size_t smem = sizeof(LmSmem);
+    ETCH_TRY(cudaFuncSetAttribute(lm_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lm_fit_kernel<<<B, 256, smem, stream>>>(markers, valid, Bm, steps0, steps1, step0, step1, damp0, damp1, params, iters, errs, prof);
     ETCH_RETURN_LAST();
 }
 

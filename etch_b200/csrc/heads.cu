@@ -360,7 +360,8 @@ ETCH_API int etch_direction_head(const float* feats, const int* up_idx, const fl
     static_assert(TOK * LDQ >= 128 * LDT, "hidden buffer must fit the QKV region");
     ETCH_TRY(cudaFuncSetAttribute(direction_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (N + 1) / 2;
-    int gx = (148 + B - 1) / B;  // one persistent CTA per SM across the whole batch (178 KB smem => 1 CTA/SM)
+    int gx = 148 / B;  // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
+    if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
     dim3 grid(gx, B);
     direction_head_kernel<<<grid, 256, smem, stream>>>(feats, up_idx, up_w, W, N, S, dir, inv, anc_w);

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256, 1) conf_head_tc_kernel(const float* __res
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = tmem_base;
+    const uint32_t tmem = umma::uniform(tmem_base);
     const int nchunk = K * 4;
     uint32_t gi = 0;  // global chunk counter (barrier phases run across tiles)
 
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256, 1) conf_head_tc_kernel(const float* __res
         umma::fence_async_smem();
         __syncthreads();
 
-        if (tid == 0) {
-            // ===== weight streaming + MMA issue =====
+        if (warp == 0) {
+            // ===== weight streaming + MMA issue (warp-collective, one elected lane executes) =====
             const uint32_t a_hi = umma::smem_u32(s_A), a_lo = a_hi + A_BYTES;
             {   // first slice of the tile: its buffer was last read by MMA (gi-2), which completed before the tile barrier
                 const uint32_t g = gi;
@@ -224,7 +224,7 @@ __device__ void dh_so3_direction(const double Ce[3][3], float out[3]) {
     for (int i = 0; i < 3; ++i) out[i] = (float)(u0[i] * v0[2] + u1[i] * v1[2] + u2[i] * v2z);
 }
 
-struct DhIssuer {   // state of the single weight-streaming / MMA-issuing thread
+struct DhIssuer {   // state of the weight-streaming / MMA-issuing warp (all fields warp-uniform)
     const float* wall;      // [18][2][16][32][4]
     unsigned char* s_B;     // [2][hi|lo]
     uint64_t* b_full;
@@ -266,55 +266,64 @@ __device__ __forceinline__ void dh_store_kv(uint32_t tmem, float* s_kv, int warp
     }
 }
 
-// softmax(q K^T) V for (token = my TMEM lane, my 4 heads); output written as (hi, lo) into the canonical O tile
+// softmax(q K^T) V for (token = my TMEM lane, my 4 heads); output written as (hi, lo) into the canonical O tile.
+// Online softmax over 3 chunks of 20 keys keeps the unrolled body small (the fully unrolled 4 x 60-key version
+// thrashed the instruction cache: stall_no_inst dominated the profile) at the cost of 3 extra exp's per head.
 __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, unsigned char* s_O, int warp, int lane) {
     const int q = warp & 3, hq = (warp >> 2) * 4;
     const int row = q * 32 + lane;
     const bool valid = row < 2 * DH_NA;
-    const int base = (row >= DH_NA ? DH_NA : 0);
-    float qall[32];   // the whole warp loads its 4 heads' queries in one converged tcgen05.ld
-    umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + hq * 8, qall);
-    if (!valid) return;
-#pragma unroll
+    const int base = (valid && row >= DH_NA) ? DH_NA : 0;
+#pragma unroll 1
     for (int hh = 0; hh < 4; ++hh) {
         const int h = hq + hh;
         float qv[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) qv[d] = qall[hh * 8 + d];
-        float s[DH_NA];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < DH_NA; ++j) {
-            const float* kr = s_kv + (base + j) * DH_LDKV + h * 8;
-            const float4 ka = *reinterpret_cast<const float4*>(kr);
-            const float4 kb = *reinterpret_cast<const float4*>(kr + 4);
-            float v = qv[0] * ka.x;
-            v = fmaf(qv[1], ka.y, v); v = fmaf(qv[2], ka.z, v); v = fmaf(qv[3], ka.w, v);
-            v = fmaf(qv[4], kb.x, v); v = fmaf(qv[5], kb.y, v); v = fmaf(qv[6], kb.z, v); v = fmaf(qv[7], kb.w, v);
-            s[j] = v;
-            mx = fmaxf(mx, v);
-        }
-        float sum = 0.f;
+        umma::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + h * 8, qv);   // warp-collective: every lane takes part
+        float mx = -INFINITY, sum = 0.f;
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int j0 = 0; j0 < DH_NA; j0 += 20) {
+            float s[20];
+            float cm = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < DH_NA; ++j) {
-            const float p = expf(s[j] - mx);
-            sum += p;
-            const float* vr = s_kv + (base + j) * DH_LDKV + 64 + h * 8;
-            const float4 va = *reinterpret_cast<const float4*>(vr);
-            const float4 vb = *reinterpret_cast<const float4*>(vr + 4);
-            o[0] = fmaf(p, va.x, o[0]); o[1] = fmaf(p, va.y, o[1]); o[2] = fmaf(p, va.z, o[2]); o[3] = fmaf(p, va.w, o[3]);
-            o[4] = fmaf(p, vb.x, o[4]); o[5] = fmaf(p, vb.y, o[5]); o[6] = fmaf(p, vb.z, o[6]); o[7] = fmaf(p, vb.w, o[7]);
+            for (int j = 0; j < 20; ++j) {
+                const float* kr = s_kv + (base + j0 + j) * DH_LDKV + h * 8;
+                const float4 ka = *reinterpret_cast<const float4*>(kr);
+                const float4 kb = *reinterpret_cast<const float4*>(kr + 4);
+                float v = qv[0] * ka.x;
+                v = fmaf(qv[1], ka.y, v); v = fmaf(qv[2], ka.z, v); v = fmaf(qv[3], ka.w, v);
+                v = fmaf(qv[4], kb.x, v); v = fmaf(qv[5], kb.y, v); v = fmaf(qv[6], kb.z, v); v = fmaf(qv[7], kb.w, v);
+                s[j] = v;
+                cm = fmaxf(cm, v);
+            }
+            const float mn = fmaxf(mx, cm);
+            const float sc = expf(mx - mn);   // first chunk: exp(-inf) = 0
+            mx = mn;
+            sum *= sc;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) o[d] *= sc;
+#pragma unroll
+            for (int j = 0; j < 20; ++j) {
+                const float p = expf(s[j] - mn);
+                sum += p;
+                const float* vr = s_kv + (base + j0 + j) * DH_LDKV + 64 + h * 8;
+                const float4 va = *reinterpret_cast<const float4*>(vr);
+                const float4 vb = *reinterpret_cast<const float4*>(vr + 4);
+                o[0] = fmaf(p, va.x, o[0]); o[1] = fmaf(p, va.y, o[1]); o[2] = fmaf(p, va.z, o[2]); o[3] = fmaf(p, va.w, o[3]);
+                o[4] = fmaf(p, vb.x, o[4]); o[5] = fmaf(p, vb.y, o[5]); o[6] = fmaf(p, vb.z, o[6]); o[7] = fmaf(p, vb.w, o[7]);
+            }
         }
-        const float inv = 1.0f / sum;
+        if (valid) {
+            const float inv = 1.0f / sum;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            float4 hi, lo;
-            umma::split_tf32(o[g * 4 + 0] * inv, hi.x, lo.x); umma::split_tf32(o[g * 4 + 1] * inv, hi.y, lo.y);
-            umma::split_tf32(o[g * 4 + 2] * inv, hi.z, lo.z); umma::split_tf32(o[g * 4 + 3] * inv, hi.w, lo.w);
-            const int kc = h * 2 + g;
-            *reinterpret_cast<float4*>(s_O + kc * (128 * 16) + row * 16) = hi;
-            *reinterpret_cast<float4*>(s_O + DH_XB + kc * (128 * 16) + row * 16) = lo;
+            for (int g = 0; g < 2; ++g) {
+                float4 hi, lo;
+                umma::split_tf32(o[g * 4 + 0] * inv, hi.x, lo.x); umma::split_tf32(o[g * 4 + 1] * inv, hi.y, lo.y);
+                umma::split_tf32(o[g * 4 + 2] * inv, hi.z, lo.z); umma::split_tf32(o[g * 4 + 3] * inv, hi.w, lo.w);
+                const int kc = h * 2 + g;
+                *reinterpret_cast<float4*>(s_O + kc * (128 * 16) + row * 16) = hi;
+                *reinterpret_cast<float4*>(s_O + DH_XB + kc * (128 * 16) + row * 16) = lo;
+            }
         }
     }
 }
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = tmem_base;
+    const uint32_t tmem = umma::uniform(tmem_base);
     const uint32_t x_hi = umma::smem_u32(s_X), x_lo = x_hi + DH_XB, o_hi = umma::smem_u32(s_O), o_lo = o_hi + DH_XB;
     DhIssuer iss{wall, s_B, b_full, b_empty, 0u, 0u, 0};
     uint32_t n_mma = 0;
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int p0 = tile * 2;
-        if (tid == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
+        if (warp == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
         // ---- 0. blend the three coarse rows into the token tile (hi/lo, canonical) ----
         {
             const int r = tid >> 1, hf = tid & 1;
@@ -398,7 +407,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             umma::fence_async_smem();
             __syncthreads();
             // ---- QKV projection: 6 slices -> D[0:192] ----
-            if (tid == 0) {
+            if (warp == 0) {
                 umma::fence_after_sync();
                 for (int c = 0; c < 6; ++c) iss.mma_slice(x_hi, x_lo, tmem + c * 32);
                 umma::commit(&bar_mma);
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             __syncthreads();
             if (layer == 0) {
                 // ---- head_combine + bias + residual -> X ----
-                if (tid == 0) {
+                if (warp == 0) {
                     umma::fence_after_sync();
                     for (int c = 0; c < 2; ++c) iss.mma_slice(o_hi, o_lo, tmem + 192 + c * 32);
                     umma::commit(&bar_mma);
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             }
         }
         // ---- fused (Linear1 o head_combine_2) + ReLU, then (so3_reg o Linear2): D[256:384] -> anchor weights ----
-        if (tid == 0) {
+        if (warp == 0) {
             umma::fence_after_sync();
             for (int c = 0; c < 4; ++c) iss.mma_slice(o_hi, o_lo, tmem + 256 + c * 32);
             umma::commit(&bar_mma);
@@ -526,7 +535,8 @@ ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const
     const size_t smem = (size_t)4 * DH_XB + (size_t)4 * DH_WB + (size_t)(2 * DH_NA * DH_LDKV + 256 + 128 + DH_NA * 9) * 4 + 128;
     ETCH_TRY(cudaFuncSetAttribute(direction_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (N + 1) / 2;
-    int gx = (148 + B - 1) / B;
+    int gx = 148 / B;   // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
+    if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
     dim3 grid(gx, B);
     direction_head_tc_kernel<<<grid, 256, smem, stream>>>(feats, up_idx, up_w, wall, bc1, bf, vreg, creg, anchors, N, S, dir, anc_w);

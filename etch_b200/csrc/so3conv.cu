@@ -178,12 +178,17 @@ __global__ void __launch_bounds__(256, 1) inter_conv_kernel(
 #pragma unroll
                     for (int i = 0; i < 6; ++i) acc[c][i] = 0.f;
                 const float* fa = F + a * CIN + c0;
+                // software pipeline: the feature row of neighbour n+1 is in flight while neighbour n is consumed
+                float4 f0 = __ldg(reinterpret_cast<const float4*>(fa + s_off[pl * NN]));
+                float4 f1 = __ldg(reinterpret_cast<const float4*>(fa + s_off[pl * NN]) + 1);
 #pragma unroll 2
                 for (int n = 0; n < NN; ++n) {
                     const float4 g = s_g[pl * NN + n];
-                    const float4* fp = reinterpret_cast<const float4*>(fa + s_off[pl * NN + n]);
-                    const float4 f0 = __ldg(fp), f1 = __ldg(fp + 1);
                     const float fv[CC] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                    if (n + 1 < NN) {
+                        const float4* fp = reinterpret_cast<const float4*>(fa + s_off[pl * NN + n + 1]);
+                        f0 = __ldg(fp); f1 = __ldg(fp + 1);
+                    }
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
                         const float w = fmaxf(fmaf(g.x, kq[i].x, fmaf(g.y, kq[i].y, fmaf(g.z, kq[i].z, g.w - kq[i].w))), 0.f);

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem = tmem_base;
+    const uint32_t tmem = umma::uniform(tmem_base);
     uint32_t n_mma = 0, n_b[2] = {0, 0};   // completed phases per barrier (uniform across threads)
     double acc_s = 0.0, acc_ss = 0.0;
     const int ntiles = (P + TP - 1) / TP;
@@ -78,9 +78,7 @@ __global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
         const int p0 = tile * TP;
         const int npts = min(TP, P - p0);
         // first weight slice of this tile (buffer 0 is free: every MMA of the previous tile has completed)
-        if (tid == 0) {
-            bulk_load(s_B, Wc, 2 * B_BYTES, &bar_b[0]);
-        }
+        if (warp == 0) bulk_load(s_B, Wc, 2 * B_BYTES, &bar_b[0]);
         // stage (and normalise) the activations of the tile's points; zero the pad rows of the A tiles
         for (int t = tid; t < NPAIR * (CIN / 4); t += 256) {
             const int row = t / (CIN / 4), c4 = t % (CIN / 4);
@@ -122,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
             }
             umma::fence_async_smem();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 const int buf = j & 1;
                 if (j + 1 < J) {  // prefetch the next slice into the other buffer (its last reader, MMA j-1, has completed)
                     bulk_load(s_B + (buf ^ 1) * 2 * B_BYTES, Wc + (size_t)(j + 1) * 2 * COUT * CIN, 2 * B_BYTES, &bar_b[buf ^ 1]);
@@ -177,7 +175,8 @@ __global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
 }
 
 int grid_for_tc(int ntiles, int B) {
-    int g = (148 + B - 1) / B;
+    int g = 148 / B;   // one wave of persistent CTAs (1 CTA/SM)
+    if (g < 1) g = 1;
     return ntiles < g ? ntiles : g;
 }
 

@@ -12,6 +12,22 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- issue-side primitives are WARP-COLLECTIVE: all 32 lanes of one (converged) warp call them with warp-uniform
+// ---- arguments and exactly one elected lane executes the instruction.  Issuing from a single divergent thread makes
+// ---- the compiler wrap every tcgen05.mma in an elect/branch loop (~50 cycles each); the warp-uniform form keeps the
+// ---- descriptors in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// broadcast lane 0's value so the compiler can treat it as warp-uniform
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // K-major, no swizzle. lbo/sbo in bytes.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -28,6 +44,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one())
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
@@ -35,8 +52,10 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         : "memory");
 }
 
-// all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)
+// all previously issued MMAs arrive on the mbarrier when complete (implies fence::before_thread_sync); warp-collective.
+// NOTE: the elected lane must be the one that issued the MMAs -- elect.sync picks the same lane for the same mask.
 __device__ __forceinline__ void commit(uint64_t* bar) {
+    if (elect_one())
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
@@ -105,13 +124,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 1-D bulk copy global -> shared through the TMA engine; completion (bytes) is signalled on `bar`
+// 1-D bulk copy global -> shared through the TMA engine; completion (bytes) is signalled on `bar` (warp-collective)
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     const uint32_t d = smem_u32(dst_smem), b = smem_u32(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(b)
-                 : "memory");
+    if (elect_one()) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(b)
+                     : "memory");
+    }
 }
 
 // fp32 -> (hi, lo) with hi = round-to-nearest tf32, lo = x - hi (exact); the tensor core truncates lo to tf32
@@ -127,16 +148,24 @@ __host__ __device__ __forceinline__ constexpr uint32_t tile_off(int r, int k, in
     return (uint32_t)((k >> 2) * (R * 16) + r * 16 + (k & 3) * 4);
 }
 
-// D[128 x N] (+)= A[128 x K] * B[N x K]^T with the 3xTF32 split; issued by ONE thread.
+// D[128 x N] (+)= A[128 x K] * B[N x K]^T with the 3xTF32 split; warp-collective (one elected lane issues).
 // a_hi/a_lo/b_hi/b_lo: shared-memory byte addresses of canonical tiles ([128 x K] and [N x K]); K % 8 == 0.
+// The four descriptors are built once; each k-step only bumps their 14-bit start-address fields (16-byte units).
 __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                                   int K, int N, bool accumulate_first) {
     const uint32_t idesc = make_idesc_tf32(128, N);
     const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)N * 16;
-    for (int ks = 0; ks < K / 8; ++ks) {
-        const uint64_t ah = make_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128), al = make_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
-        const uint64_t bh = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128), bl = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
-        mma_tf32(tmem_d, ah, bh, idesc, (ks > 0 || accumulate_first) ? 1u : 0u);
+    uint64_t ah = make_desc(a_hi, lbo_a, 128), al = make_desc(a_lo, lbo_a, 128);
+    uint64_t bh = make_desc(b_hi, lbo_b, 128), bl = make_desc(b_lo, lbo_b, 128);
+    const uint64_t da = (uint64_t)((2 * lbo_a) >> 4), db = (uint64_t)((2 * lbo_b) >> 4);
+    mma_tf32(tmem_d, ah, bh, idesc, accumulate_first ? 1u : 0u);
+    mma_tf32(tmem_d, al, bh, idesc, 1u);
+    mma_tf32(tmem_d, ah, bl, idesc, 1u);
+    const int nk = K / 8;
+#pragma unroll 4
+    for (int ks = 1; ks < nk; ++ks) {
+        ah += da; al += da; bh += db; bl += db;
+        mma_tf32(tmem_d, ah, bh, idesc, 1u);
         mma_tf32(tmem_d, al, bh, idesc, 1u);
         mma_tf32(tmem_d, ah, bl, idesc, 1u);
     }
