@@ -205,10 +205,21 @@ class PTGeometry:
         return idx, d2
 
 
+_TC_WEIGHTS = {}  # data_ptr of a transposed weight -> its tensor-core block layout (built once per checkpoint/device)
+
+
 def _linear(X, Wt, scale=None, shift=None, R=None, relu=False, seg=None, seg_off=None):
     n, ci = X.shape
     co = Wt.shape[1]
     Y = torch.empty(n, co, dtype=torch.float32, device=X.device)
+    if USE_TC and ci >= 16 and 16 <= co <= 512:
+        key = (Wt.data_ptr(), tuple(Wt.shape), str(Wt.device))
+        Wc = _TC_WEIGHTS.get(key)
+        if Wc is None:
+            Wc = _TC_WEIGHTS[key] = (tc.tc_linear_weights(Wt, Wt.device), Wt)  # keep Wt alive so the pointer stays unique
+        L.call("linear_tc", L.ptr(X), ci, L.ptr(Wc[0]), n, ci, co, L.ptr(scale), L.ptr(shift), L.ptr(R), L.ptr(seg), L.ptr(seg_off),
+               0 if seg_off is None else int(seg_off.shape[0]), 1 if relu else 0, L.ptr(Y), co)
+        return Y
     L.call("linear", L.ptr(X), ci, L.ptr(Wt), n, ci, co, L.ptr(scale), L.ptr(shift), L.ptr(R), L.ptr(seg), L.ptr(seg_off),
            0 if seg_off is None else int(seg_off.shape[0]), 1 if relu else 0, L.ptr(Y), co)
     return Y

@@ -30,3 +30,14 @@ def tc_operand_chunks(w_nk, kchunk, device):
     """[N,K] -> [K/kchunk, 2, kchunk/4, N, 4]: one (hi, lo) tile pair per K-chunk, each contiguous for a bulk copy."""
     n, k = w_nk.shape
     return torch.stack([tc_operand(w_nk[:, c:c + kchunk], "cpu") for c in range(0, k, kchunk)], 0).contiguous().to(device)
+
+
+def tc_linear_weights(wt_ci_co, device):
+    """Wt [ci, co] (the transposed nn.Linear weight used by etch_linear) -> [KC, NC, 2, 16, 64, 4] blocks for etch_linear_tc."""
+    w = wt_ci_co.detach().float().cpu().t().contiguous()  # [co, ci]
+    co, ci = w.shape
+    KC, NC = (ci + 63) // 64, (co + 63) // 64
+    wp = torch.zeros(NC * 64, KC * 64)
+    wp[:co, :ci] = w
+    blocks = [[tc_operand(wp[nc * 64:(nc + 1) * 64, kc * 64:(kc + 1) * 64], "cpu") for nc in range(NC)] for kc in range(KC)]
+    return torch.stack([torch.stack(b, 0) for b in blocks], 0).contiguous().to(device)
