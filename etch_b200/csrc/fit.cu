@@ -368,8 +368,9 @@ __device__ void lm_jacobian(LmSmem& S, const BodyMarkers& Bm, int nb) {
 // row so that y = L^-1 b falls out of the factorisation), accumulates it from J in registers, and the right-looking
 // blocked Cholesky runs on those registers with two barriers per block column; a single warp then does the blocked
 // back-substitution L^T x = y.
-__device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
+__device__ void lm_solve(LmSmem& S, int rows, int D, float lambda, long long* tprof) {
     const int tid = threadIdx.x;
+    const long long tc0 = clock64();
     const int NT = (D + TS - 1) / TS;
     const int NTL = NT * (NT + 1) / 2;
     int ta = -1, tb = -1;      // block row / column of my tile; ta == NT marks a right-hand-side tile
@@ -409,6 +410,8 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
             for (int j = 0; j < TS; ++j) acc[0][j] = fmaf(tb * TS + j < D ? row[tb * TS + j] : 0.f, -rr, acc[0][j]);
         }
     }
+    __syncthreads();
+    const long long tc1 = clock64();
     for (int kb = 0; kb < NT; ++kb) {
         if (ta == kb && tb == kb) {
 #pragma unroll
@@ -497,6 +500,7 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
         }
     }
     __syncthreads();
+    const long long tc2 = clock64();
     // blocked back-substitution L^T x = y (y = row D of A), one warp; lane l accumulates the tiles of block rows kb+1+l, ...
     if (tid < 32) {
         for (int i = tid; i < NT * TS; i += 32) S.g[i] = i < D ? S.A[D * LDA + i] : 0.f;
@@ -537,6 +541,7 @@ __device__ void lm_solve(LmSmem& S, int rows, int D, float lambda) {
         }
     }
     __syncthreads();
+    if (tprof && tid == 0) { tprof[0] += tc1 - tc0; tprof[1] += tc2 - tc1; tprof[2] += clock64() - tc2; }
 }
 
 __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict__ markers, const unsigned char* __restrict__ valid,
@@ -569,11 +574,13 @@ __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict_
         float last = S.err;
         int done = 0;
         long long t_eval = 0, t_jac = 0, t_solve = 0;
+        __shared__ long long tsolve[3];
+        if (tid == 0) { tsolve[0] = tsolve[1] = tsolve[2] = 0; }
         for (int it = 0; it < maxit; ++it) {
             long long c0 = clock64();
             lm_jacobian(S, Bm, nb);
             long long c1 = clock64();
-            lm_solve(S, M * 3, D, lambda);
+            lm_solve(S, M * 3, D, lambda, prof ? tsolve : nullptr);
             long long c2 = clock64();
             t_jac += c1 - c0; t_solve += c2 - c1;
             // x <- x + step * delta   (columns: theta | beta[0..nb) | transl)
@@ -594,7 +601,8 @@ __global__ void __launch_bounds__(256, 1) lm_fit_kernel(const float* __restrict_
         }
         if (tid == 0) {
             iters[b * 2 + stage] = done; errs[b * 2 + stage] = S.err;
-            if (prof) { prof[(b * 2 + stage) * 3] = t_eval; prof[(b * 2 + stage) * 3 + 1] = t_jac; prof[(b * 2 + stage) * 3 + 2] = t_solve; }
+            if (prof) { prof[(b * 2 + stage) * 6] = t_eval; prof[(b * 2 + stage) * 6 + 1] = t_jac; prof[(b * 2 + stage) * 6 + 2] = t_solve;
+                        prof[(b * 2 + stage) * 6 + 3] = tsolve[0]; prof[(b * 2 + stage) * 6 + 4] = tsolve[1]; prof[(b * 2 + stage) * 6 + 5] = tsolve[2]; }
         }
         __syncthreads();
     }

@@ -166,14 +166,14 @@ ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float*
 //   D[256:384] = O  (W1 Wc2)^T        (layer 2 output folded with Linear1; ReLU and the 128->1 map are applied straight
 //                                      from TMEM, the hidden layer is never stored)
 // Activations live in shared memory as (hi, lo) TF32 pairs in the canonical UMMA layout (x == hi + lo exactly), weights
-// stream as 18 pre-split 32-row slices per tile through a 2-deep cp.async.bulk ring.  The softmax attention itself is
+// stream as 18 pre-split [64 rows x 32 k] slices per tile through a 2-deep cp.async.bulk ring.  The softmax attention itself is
 // block-diagonal (60x60 per point and head) and stays on the CUDA cores.
 namespace {
 
 constexpr int DH_NA = 60;
 constexpr int DH_LDKV = 132;                       // floats per row of the K|V tile
 constexpr uint32_t DH_XB = 128 * 64 * 4;           // bytes of one canonical [128 x 64] tile
-constexpr uint32_t DH_WB = 32 * 64 * 4;            // bytes of one (hi or lo) weight slice [32 x 64]
+constexpr uint32_t DH_WB = 64 * 32 * 4;            // bytes of one (hi or lo) weight slice [64 rows x 32 k]
 constexpr int DH_NCHUNK = 18;
 
 __device__ void dh_jacobi3(double A[3][3], double V[3][3], double e[3]) {
@@ -225,7 +225,7 @@ __device__ void dh_so3_direction(const double Ce[3][3], float out[3]) {
 }
 
 struct DhIssuer {   // state of the weight-streaming / MMA-issuing warp (all fields warp-uniform)
-    const float* wall;      // [18][2][16][32][4]
+    const float* wall;      // [18][2][8][64][4]: 9 blocks of 64 output rows x 2 K-halves, (hi, lo) canonical tiles
     unsigned char* s_B;     // [2][hi|lo]
     uint64_t* b_full;
     uint64_t* b_empty;
@@ -235,18 +235,22 @@ struct DhIssuer {   // state of the weight-streaming / MMA-issuing warp (all fie
         if (ld >= DH_NCHUNK) return;
         const uint32_t buf = gl & 1;
         if (gl >= 2) umma::mbar_wait(&b_empty[buf], ((gl - 2) >> 1) & 1);
-        umma::bulk_load(s_B + buf * 2 * DH_WB, wall + (size_t)ld * 2 * 32 * 64, 2 * DH_WB, &b_full[buf]);
+        umma::bulk_load(s_B + buf * 2 * DH_WB, wall + (size_t)ld * 2 * 64 * 32, 2 * DH_WB, &b_full[buf]);
         ++ld; ++gl;
     }
-    __device__ void mma_slice(uint32_t a_hi, uint32_t a_lo, uint32_t tmem_d) {
-        const uint32_t buf = gm & 1;
-        umma::mbar_wait(&b_full[buf], (gm >> 1) & 1);
-        umma::fence_after_sync();
-        const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * DH_WB), b_lo = b_hi + DH_WB;
-        umma::issue_gemm_3xtf32(tmem_d, a_hi, a_lo, b_hi, b_lo, 64, 32, false);
-        umma::commit(&b_empty[buf]);
-        ++gm;
-        load_next();
+    // one 64-column block of the output = two slices (K halves 0..31, 32..63) accumulated into tmem_d[0:64]
+    __device__ void mma_block(uint32_t a_hi, uint32_t a_lo, uint32_t tmem_d) {
+        for (int kh = 0; kh < 2; ++kh) {
+            const uint32_t buf = gm & 1;
+            umma::mbar_wait(&b_full[buf], (gm >> 1) & 1);
+            umma::fence_after_sync();
+            const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * DH_WB), b_lo = b_hi + DH_WB;
+            // K-half kh of the canonical [128 x 64] A tile starts (32/4) k-chunks = 8 * 2048 bytes in
+            umma::issue_gemm_3xtf32(tmem_d, a_hi + kh * 8 * 2048, a_lo + kh * 8 * 2048, b_hi, b_lo, 32, 64, kh > 0);
+            umma::commit(&b_empty[buf]);
+            ++gm;
+            load_next();
+        }
     }
 };
 
@@ -331,7 +335,7 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
 __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     const float* __restrict__ feats,   // [B,S,60,64]
     const int* __restrict__ up_idx, const float* __restrict__ up_w,   // [B,N,3]
-    const float* __restrict__ wall,    // [18][2][16][32][4] weight slices
+    const float* __restrict__ wall,    // [18][2][8][64][4] weight slices
     const float* __restrict__ bc1,     // [64]
     const float* __restrict__ bf,      // [128]
     const float* __restrict__ vreg,    // [128]
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             // ---- QKV projection: 6 slices -> D[0:192] ----
             if (warp == 0) {
                 umma::fence_after_sync();
-                for (int c = 0; c < 6; ++c) iss.mma_slice(x_hi, x_lo, tmem + c * 32);
+                for (int c = 0; c < 3; ++c) iss.mma_block(x_hi, x_lo, tmem + c * 64);
                 umma::commit(&bar_mma);
             }
             umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
                 // ---- head_combine + bias + residual -> X ----
                 if (warp == 0) {
                     umma::fence_after_sync();
-                    for (int c = 0; c < 2; ++c) iss.mma_slice(o_hi, o_lo, tmem + 192 + c * 32);
+                    iss.mma_block(o_hi, o_lo, tmem + 192);
                     umma::commit(&bar_mma);
                 }
                 umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
         // ---- fused (Linear1 o head_combine_2) + ReLU, then (so3_reg o Linear2): D[256:384] -> anchor weights ----
         if (warp == 0) {
             umma::fence_after_sync();
-            for (int c = 0; c < 4; ++c) iss.mma_slice(o_hi, o_lo, tmem + 256 + c * 32);
+            for (int c = 0; c < 2; ++c) iss.mma_block(o_hi, o_lo, tmem + 256 + c * 64);
             umma::commit(&bar_mma);
         }
         umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(256) interp_inv_kernel(const float* __restrict
 
 }  // namespace
 
-// Tensor-core decode_direction. wall = the 18 weight slices [18][2][16][32][4] (see etch_b200/models/heads.py::DirectionPlan).
+// Tensor-core decode_direction. wall = the 18 weight slices [18][2][8][64][4] (see etch_b200/models/heads.py::DirectionPlan).
 // fmean_scratch [B,S,64] is caller-owned scratch for the per-coarse-point anchor mean.
 ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const float* up_w, const float* wall,
                                     const float* bc1, const float* bf, const float* vreg, float creg, const float* anchors,

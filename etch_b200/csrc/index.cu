@@ -208,7 +208,7 @@ constexpr int KNN_TILE = 512;
 
 // NS > 0: compile-time heap size; NS == 0: runtime nsample (<= 100, as the reference's best_dist[100])
 template <int NS>
-__global__ void __launch_bounds__(128) knn_packed_kernel(int m, int nsample_rt, const float* __restrict__ xyz,
+__global__ void __launch_bounds__(64) knn_packed_kernel(int m, int nsample_rt, const float* __restrict__ xyz,
                                                          const float* __restrict__ new_xyz, const int* __restrict__ offset,
                                                          const int* __restrict__ new_offset, int nbatch,
                                                          int* __restrict__ idx, float* __restrict__ dist2) {
@@ -245,7 +245,26 @@ __global__ void __launch_bounds__(128) knn_packed_kernel(int m, int nsample_rt, 
         __syncthreads();
         if (active) {
             const int a = max(start, t0) - t0, e = min(end, t0 + cntp) - t0;
-            for (int i = a; i < e; ++i) {
+            int i = a;
+            // 4 candidates per trip: the common case (none beats the heap root) costs one compare; insertions replay the
+            // candidates in index order against the *current* root, exactly like the reference's serial scan
+            for (; i + 3 < e; i += 4) {
+                float d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d[u] = etch_sqdist3(qx - tile[(i + u) * 3], qy - tile[(i + u) * 3 + 1], qz - tile[(i + u) * 3 + 2]);
+                if (fminf(fminf(d[0], d[1]), fminf(d[2], d[3])) < root) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (d[u] < root) {
+                            best_dist[0] = d[u];
+                            best_idx[0] = t0 + i + u;
+                            knn_reheap<NS>(best_dist, best_idx, nsample);
+                            root = best_dist[0];
+                        }
+                    }
+                }
+            }
+            for (; i < e; ++i) {
                 const float d2 = etch_sqdist3(qx - tile[i * 3], qy - tile[i * 3 + 1], qz - tile[i * 3 + 2]);
                 if (d2 < root) {
                     best_dist[0] = d2;
@@ -341,11 +360,11 @@ ETCH_API int etch_knn_packed(int m, int nsample, const float* xyz, const float* 
                              const int* new_offset, int nbatch, int* idx, float* dist2, cudaStream_t stream) {
     if (!xyz || !new_xyz || !offset || !new_offset || !idx || !dist2 || m <= 0 || nsample <= 0 || nsample > 100 || nbatch <= 0)
         return ETCH_EINVAL;
-    const int grid = etch_cdiv(m, 128);
-    if (nsample == 3) knn_packed_kernel<3><<<grid, 128, 0, stream>>>(m, 3, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
-    else if (nsample == 8) knn_packed_kernel<8><<<grid, 128, 0, stream>>>(m, 8, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
-    else if (nsample == 16) knn_packed_kernel<16><<<grid, 128, 0, stream>>>(m, 16, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
-    else knn_packed_kernel<0><<<grid, 128, 0, stream>>>(m, nsample, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    const int grid = etch_cdiv(m, 64);
+    if (nsample == 3) knn_packed_kernel<3><<<grid, 64, 0, stream>>>(m, 3, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else if (nsample == 8) knn_packed_kernel<8><<<grid, 64, 0, stream>>>(m, 8, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else if (nsample == 16) knn_packed_kernel<16><<<grid, 64, 0, stream>>>(m, 16, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else knn_packed_kernel<0><<<grid, 64, 0, stream>>>(m, nsample, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
     ETCH_RETURN_LAST();
 }
 

@@ -98,6 +98,9 @@ struct AttnW {
     const float* ho;   // [c]  shift
 };
 
+// One CTA walks over points; for each point the 8 warps take one neighbour each (logits), then the CTA does the
+// softmax over neighbours and a channel-parallel aggregation.  (A warp-per-point mapping left the deep levels -- 152
+// points x 512 channels -- on 19 SMs with a 50k-instruction serial chain per warp.)
 template <int R>  // R = c / 32
 __global__ void __launch_bounds__(256) pt_attn_kernel(const float* __restrict__ p, const float* __restrict__ qkv,
                                                       const int* __restrict__ idx, AttnW W, int n, int ns,
@@ -105,15 +108,14 @@ __global__ void __launch_bounds__(256) pt_attn_kernel(const float* __restrict__ 
     constexpr int C = R * 32, T = C / 8, TL = (T + 31) / 32;
     extern __shared__ __align__(16) float sm[];
     float* s_W1 = sm;                 // [T][C]
-    float* s_log = sm + T * C;        // [8 warps][16][T]
+    float* s_W2 = s_W1 + T * C;       // [T][T]
+    float* s_lg = s_W2 + T * T;       // [16][T] logits -> softmax weights
+    float* s_q = s_lg + 16 * T;       // [C]
+    float* s_e = s_q + C;             // [16][4] relu(P0 d + b)
+    int* s_nb = reinterpret_cast<int*>(s_e + 64);  // [16]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < T * C; i += 256) s_W1[i] = __ldg(W.W1 + i);
-    __syncthreads();
-    float P0[9], p0b[3];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) P0[i] = __ldg(W.P0 + i);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) p0b[i] = __ldg(W.p0b + i);
+    for (int i = tid; i < T * T; i += 256) s_W2[i] = __ldg(W.W2 + i);
     float P3[R][3], p3b[R], s0[R], h0[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -121,26 +123,31 @@ __global__ void __launch_bounds__(256) pt_attn_kernel(const float* __restrict__ 
         P3[r][0] = __ldg(W.P3 + ch * 3); P3[r][1] = __ldg(W.P3 + ch * 3 + 1); P3[r][2] = __ldg(W.P3 + ch * 3 + 2);
         p3b[r] = __ldg(W.p3b + ch); s0[r] = __ldg(W.s0 + ch); h0[r] = __ldg(W.h0 + ch);
     }
-    float* lg = s_log + warp * 16 * T;
-    for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
-        const float pix = __ldg(p + (size_t)i * 3), piy = __ldg(p + (size_t)i * 3 + 1), piz = __ldg(p + (size_t)i * 3 + 2);
-        float qv[R];
+    __syncthreads();
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        // ---- A: neighbour geometry + query row ----
+        if (tid < ns) {
+            const int nb = __ldg(idx + (size_t)i * ns + tid);
+            const float dx = __ldg(p + (size_t)nb * 3) - __ldg(p + (size_t)i * 3), dy = __ldg(p + (size_t)nb * 3 + 1) - __ldg(p + (size_t)i * 3 + 1),
+                        dz = __ldg(p + (size_t)nb * 3 + 2) - __ldg(p + (size_t)i * 3 + 2);
+            s_nb[tid] = nb;
 #pragma unroll
-        for (int r = 0; r < R; ++r) qv[r] = __ldg(qkv + (size_t)i * 3 * C + lane + 32 * r);
-        // ---- pass 1: attention logits per (neighbour, shared plane) ----
-        for (int j = 0; j < ns; ++j) {
-            const int nb = __ldg(idx + (size_t)i * ns + j);
-            const float dx = __ldg(p + (size_t)nb * 3) - pix, dy = __ldg(p + (size_t)nb * 3 + 1) - piy,
-                        dz = __ldg(p + (size_t)nb * 3 + 2) - piz;
-            float e[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) e[a] = fmaxf(fmaf(P0[a * 3 + 2], dz, fmaf(P0[a * 3 + 1], dy, fmaf(P0[a * 3], dx, p0b[a]))), 0.f);
+            for (int a = 0; a < 3; ++a)
+                s_e[tid * 4 + a] = fmaxf(fmaf(__ldg(W.P0 + a * 3 + 2), dz, fmaf(__ldg(W.P0 + a * 3 + 1), dy, fmaf(__ldg(W.P0 + a * 3), dx, __ldg(W.p0b + a)))), 0.f);
+        }
+        for (int ch = tid; ch < C; ch += 256) s_q[ch] = __ldg(qkv + (size_t)i * 3 * C + ch);
+        __syncthreads();
+        // ---- B: logits, one neighbour per warp ----
+        for (int j = warp; j < ns; j += 8) {
+            const int nb = s_nb[j];
+            const float e0 = s_e[j * 4], e1 = s_e[j * 4 + 1], e2 = s_e[j * 4 + 2];
             float wp[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float pr = fmaf(P3[r][2], e[2], fmaf(P3[r][1], e[1], fmaf(P3[r][0], e[0], p3b[r])));
-                const float kv = __ldg(qkv + (size_t)nb * 3 * C + C + lane + 32 * r);
-                wp[r] = fmaxf(fmaf(kv - qv[r] + pr, s0[r], h0[r]), 0.f);
+                const int ch = lane + 32 * r;
+                const float pr = fmaf(P3[r][2], e2, fmaf(P3[r][1], e1, fmaf(P3[r][0], e0, p3b[r])));
+                const float kv = __ldg(qkv + (size_t)nb * 3 * C + C + ch);
+                wp[r] = fmaxf(fmaf(kv - s_q[ch] + pr, s0[r], h0[r]), 0.f);
             }
             float hh[TL];
 #pragma unroll
@@ -153,7 +160,6 @@ __global__ void __launch_bounds__(256) pt_attn_kernel(const float* __restrict__ 
                 for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
                 if ((t & 31) == lane) hh[t >> 5] = fmaxf(part + __ldg(W.b1 + t), 0.f);
             }
-            // second small linear T -> T (each lane owns outputs t' = lane, lane+32)
             float o2[TL];
 #pragma unroll
             for (int u = 0; u < TL; ++u) o2[u] = (lane + 32 * u < T) ? __ldg(W.b2 + lane + 32 * u) : 0.f;
@@ -161,52 +167,35 @@ __global__ void __launch_bounds__(256) pt_attn_kernel(const float* __restrict__ 
                 const float hv = __shfl_sync(0xffffffffu, hh[t >> 5], t & 31);
 #pragma unroll
                 for (int u = 0; u < TL; ++u)
-                    if (lane + 32 * u < T) o2[u] = fmaf(__ldg(W.W2 + (lane + 32 * u) * T + t), hv, o2[u]);
+                    if (lane + 32 * u < T) o2[u] = fmaf(s_W2[(lane + 32 * u) * T + t], hv, o2[u]);
             }
 #pragma unroll
             for (int u = 0; u < TL; ++u)
-                if (lane + 32 * u < T) lg[j * T + lane + 32 * u] = o2[u];
+                if (lane + 32 * u < T) s_lg[j * T + lane + 32 * u] = o2[u];
         }
-        __syncwarp();
-        // ---- softmax over the neighbours, per shared plane ----
-#pragma unroll
-        for (int u = 0; u < TL; ++u) {
-            const int t = lane + 32 * u;
-            if (t < T) {
-                float mx = -INFINITY;
-                for (int j = 0; j < ns; ++j) mx = fmaxf(mx, lg[j * T + t]);
-                float s = 0.f;
-                for (int j = 0; j < ns; ++j) { const float ev = expf(lg[j * T + t] - mx); lg[j * T + t] = ev; s += ev; }
-                const float inv = 1.0f / s;
-                for (int j = 0; j < ns; ++j) lg[j * T + t] *= inv;
+        __syncthreads();
+        // ---- C: softmax over the neighbours, per shared plane ----
+        if (tid < T) {
+            float mx = -INFINITY;
+            for (int j = 0; j < ns; ++j) mx = fmaxf(mx, s_lg[j * T + tid]);
+            float s = 0.f;
+            for (int j = 0; j < ns; ++j) { const float ev = expf(s_lg[j * T + tid] - mx); s_lg[j * T + tid] = ev; s += ev; }
+            const float inv = 1.0f / s;
+            for (int j = 0; j < ns; ++j) s_lg[j * T + tid] *= inv;
+        }
+        __syncthreads();
+        // ---- D: aggregate (v + p_r) with the shared-plane weights, channel-parallel; bn2 + ReLU epilogue ----
+        for (int ch = tid; ch < C; ch += 256) {
+            const float a0 = __ldg(W.P3 + ch * 3), a1 = __ldg(W.P3 + ch * 3 + 1), a2 = __ldg(W.P3 + ch * 3 + 2), ab = __ldg(W.p3b + ch);
+            float acc = 0.f;
+            for (int j = 0; j < ns; ++j) {
+                const float pr = fmaf(a2, s_e[j * 4 + 2], fmaf(a1, s_e[j * 4 + 1], fmaf(a0, s_e[j * 4], ab)));
+                const float vv = __ldg(qkv + (size_t)s_nb[j] * 3 * C + 2 * C + ch);
+                acc = fmaf(vv + pr, s_lg[j * T + (ch % T)], acc);
             }
+            out[(size_t)i * C + ch] = fmaxf(fmaf(acc, __ldg(W.so + ch), __ldg(W.ho + ch)), 0.f);
         }
-        __syncwarp();
-        // ---- pass 2: aggregate (v + p_r) with the shared-plane weights ----
-        float acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
-        for (int j = 0; j < ns; ++j) {
-            const int nb = __ldg(idx + (size_t)i * ns + j);
-            const float dx = __ldg(p + (size_t)nb * 3) - pix, dy = __ldg(p + (size_t)nb * 3 + 1) - piy,
-                        dz = __ldg(p + (size_t)nb * 3 + 2) - piz;
-            float e[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) e[a] = fmaxf(fmaf(P0[a * 3 + 2], dz, fmaf(P0[a * 3 + 1], dy, fmaf(P0[a * 3], dx, p0b[a]))), 0.f);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int ch = lane + 32 * r;
-                const float pr = fmaf(P3[r][2], e[2], fmaf(P3[r][1], e[1], fmaf(P3[r][0], e[0], p3b[r])));
-                const float vv = __ldg(qkv + (size_t)nb * 3 * C + 2 * C + ch);
-                acc[r] = fmaf(vv + pr, lg[j * T + (ch % T)], acc[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int ch = lane + 32 * r;
-            out[(size_t)i * C + ch] = fmaxf(fmaf(acc[r], __ldg(W.so + ch), __ldg(W.ho + ch)), 0.f);
-        }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -412,9 +401,10 @@ ETCH_API int etch_pt_attention(const float* p, const float* qkv, const int* idx,
     if (!p || !qkv || !idx || !out || n <= 0 || ns <= 0 || ns > 16) return ETCH_EINVAL;
     AttnW W{P0, p0b, P3, p3b, s0, h0, W1, b1, W2, b2, so, ho};
     const int T = c / 8;
-    const size_t smem = ((size_t)T * c + (size_t)8 * 16 * T) * 4;
-    int grid = etch_cdiv(n, 8);
-    if (grid > 148 * 8) grid = 148 * 8;
+    const size_t smem = ((size_t)T * c + (size_t)T * T + (size_t)16 * T + c + 64 + 16) * 4;
+    int grid = n;
+    const int per_sm = smem > 110 * 1024 ? 1 : (smem > 50 * 1024 ? 2 : 4);
+    if (grid > 148 * per_sm) grid = 148 * per_sm;
 #define ATT(R)                                                                                                   \
     {                                                                                                            \
         auto kern = pt_attn_kernel<R>;                                                                           \

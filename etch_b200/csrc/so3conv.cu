@@ -166,8 +166,11 @@ __global__ void __launch_bounds__(256, 1) inter_conv_kernel(
 
         for (int c0 = 0; c0 < CIN; c0 += CC) {
             // ---- GEMM1: y[(c,k)][pair] = sum_n f[nbr_n][a][c] * w[a][k][n], task = (pair, 6 kernel points)
-            for (int t = tid; t < NPAIR * 4; t += 256) {
-                const int pair = t % NPAIR, kg = t / NPAIR;
+            // task = (pair, group of 6 kernel points).  A warp covers 8 consecutive pairs x the 4 groups, so the 4 lanes
+            // sharing a pair read the same feature sectors (one L1 wavefront instead of four) and a warp-wide LDG touches
+            // 8 cache lines instead of 32 -- the kernel was L1tex-wavefront bound with the (pair-major) mapping.
+            for (int grp = (tid >> 5); grp < NPAIR / 8; grp += 8) {
+                const int pair = grp * 8 + (tid & 7), kg = (tid >> 3) & 3;
                 const int pl = pair / NA, a = pair % NA;
                 float4 kq[6];
 #pragma unroll

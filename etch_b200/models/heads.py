@@ -43,7 +43,7 @@ class DirectionPlan:
         self.vreg = (w2.t() @ wr).contiguous().to(**dev)          # [128]      so3_reg o Linear2
         self.creg = float(b2 @ wr + br[0])
         self.anchors = anchors.reshape(60, 9).contiguous().to(**dev)
-        # tensor-core operands: 18 slices of 32 output rows x 64 inputs, in consumption order
+        # tensor-core operands: 9 blocks of 64 output rows x 64 inputs, in consumption order
         #   layer 0: Wq/sqrt(dk), Wk, Wv (2 slices each), head_combine (2); layer 1: Wq/sqrt(dk), Wk, Wv (6); Linear1 o head_combine (4)
         def rows(layer):
             pre = "direction_encoder.self_attention_layers.%d." % layer
@@ -52,7 +52,9 @@ class DirectionPlan:
         mats = rows(0) + [f64("direction_encoder.self_attention_layers.0.head_combine.weight")] + rows(1) + [w1 @ wc2]
         allrows = torch.cat(mats, 0).float()          # [576, 64]
         assert allrows.shape == (576, 64)
-        self.wall = torch.stack([tc.tc_operand(allrows[i * 32:(i + 1) * 32], "cpu") for i in range(18)], 0).contiguous().to(device)
+        # 9 blocks of 64 output rows, each split in two K halves (32 inputs): [18][2][8][64][4]
+        self.wall = torch.stack([tc.tc_operand(allrows[(i // 2) * 64:(i // 2 + 1) * 64, (i % 2) * 32:(i % 2 + 1) * 32], "cpu")
+                                 for i in range(18)], 0).contiguous().to(device)
 
 
 def run_direction(plan, hitpts, xyz2_b3s, feats2, want_anchor_weights=False):

@@ -29,7 +29,7 @@ g = torch.Generator().manual_seed(0)
 markers = (0.3 * torch.randn(B, 86, 3, generator=g)).to(dev)
 valid = torch.ones(B, 86, dtype=torch.uint8, device=dev)
 params = torch.empty(B, 85, device=dev); iters = torch.empty(B, 2, dtype=torch.int32, device=dev); errs = torch.empty(B, 2, device=dev)
-prof = torch.zeros(B, 2, 3, dtype=torch.int64, device=dev)
+prof = torch.zeros(B, 2, 6, dtype=torch.int64, device=dev)
 for _ in range(2):
     L.call("lm_fit_profile", L.ptr(markers), L.ptr(valid), L.ptr(T.Tm), L.ptr(T.Sm), L.ptr(T.Pm), L.ptr(T.Wm), L.ptr(T.Jt), L.ptr(T.Js),
            L.ptr(T.parents), L.ptr(T.ancmask), B, T.M, 30, 50, L.f32(0.5), L.f32(0.2), L.f32(0.01), L.f32(1e-3), L.ptr(params), L.ptr(iters),
@@ -37,5 +37,5 @@ for _ in range(2):
 torch.cuda.synchronize()
 p = prof.cpu().numpy().astype(np.float64)
 it = iters.cpu().numpy()
-print("LM iters", it[0].tolist(), "cycles per iteration [eval, jacobian, solve] stage0:", (p[0, 0] / it[0, 0]).round().tolist(),
+print("LM iters", it[0].tolist(), "cycles per iteration [eval, jacobian, solve, JtJ, factor, backsub] stage0:", (p[0, 0] / it[0, 0]).round().tolist(),
       "stage1:", (p[0, 1] / it[0, 1]).round().tolist())
