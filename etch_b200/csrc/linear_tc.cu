@@ -2,68 +2,60 @@
 //     Y[n, co] = relu?( (X[n, ci] W^T + seg[segment(row)]) * scale + shift + R )
 // i.e. nn.Linear / Conv1d(k=1) + eval BatchNorm1d (folded) + residual + ReLU in one launch
 // (src/models/pointtransformer_seg.py:40-51,71-80,101-112,144-145,222).  Same contract as etch_linear (pt.cu), but the
-// GEMM runs on tcgen05 (3xTF32, fp32-level accuracy) with the [128 x co] accumulator living in TMEM.
+// GEMM runs on tcgen05 (3xTF32, fp32-level accuracy) with the accumulator in TMEM.
 //
-// One CTA = 128 rows.  K is walked in 64-wide chunks: all threads stage the X chunk (TF32 hi/lo split, canonical
-// layout, double-buffered), warp 0 streams the pre-split 64x64 weight blocks through a 2-deep cp.async.bulk ring and
-// issues the MMAs for every 64-column block of the output, so X is read exactly once.  Epilogue straight from TMEM.
+// WEIGHT-STATIONARY: a CTA owns NB output columns, bulk-copies their pre-split (hi, lo) weight tile [NB x Kpad] into
+// shared memory once, and then streams 128-row tiles of X through it: every 32-wide K chunk of the tile is staged
+// (TF32 split, canonical layout, double-buffered) by all threads while warp 0 issues the MMAs of the previous chunk.
+// Weights are therefore read from L2 once per CTA instead of once per row tile, and X is read NG = co_pad/NB times.
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace {
 
-constexpr uint32_t LT_A = 128 * 64 * 4;   // bytes of one (hi|lo) X chunk  [128 x 64]
-constexpr uint32_t LT_B = 64 * 64 * 4;    // bytes of one (hi|lo) weight block [64 x 64]
+constexpr uint32_t LT_A = 128 * 32 * 4;   // bytes of one (hi|lo) X chunk [128 rows x 32 k]
 
 __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ Wc,
-                                                           int n, int ci, int co, int KC, int NC,
+                                                           int n, int ci, int co, int Kpad, int NB,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ R, const float* __restrict__ seg,
                                                            const int* __restrict__ seg_off, int nseg, int relu,
                                                            float* __restrict__ Y, int ldy, int tcols) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* s_A = smem_raw;                 // [2 buffers][hi|lo]
-    unsigned char* s_B = s_A + 4 * LT_A;           // [2 slots][hi|lo]
-    __shared__ uint64_t a_free[2], b_full[2], b_empty[2], acc_full;
+    unsigned char* s_W = s_A + 4 * LT_A;           // [hi|lo] [Kpad/4][NB][4]
+    __shared__ uint64_t a_free[2], w_full, acc_full;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp_col0 = blockIdx.y * NB;
+    const uint32_t W_BYTES = (uint32_t)NB * Kpad * 4;     // one (hi or lo) tile
     if (warp == 0) umma::tmem_alloc(&tmem_base, tcols);
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&a_free[i], 1); umma::mbar_init(&b_full[i], 1); umma::mbar_init(&b_empty[i], 1); }
-        umma::mbar_init(&acc_full, 1);
-    }
+    if (tid == 0) { umma::mbar_init(&a_free[0], 1); umma::mbar_init(&a_free[1], 1); umma::mbar_init(&w_full, 1); umma::mbar_init(&acc_full, 1); }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = umma::uniform(tmem_base);
-    uint32_t ga = 0;            // A chunks staged so far (buffer = ga & 1), uniform across threads
-    uint32_t gl = 0, gm = 0;    // weight blocks loaded / consumed (warp 0 only)
-    uint32_t nacc = 0;          // tiles finished
-    const int nblk = KC * NC;
+    if (warp == 0) {   // weights of this column group: one bulk copy per (hi|lo) tile, chunked to stay under the tx-count limit
+        umma::bulk_load_region(s_W, Wc + (size_t)blockIdx.y * 2 * NB * Kpad, 2 * W_BYTES, &w_full);
+    }
+    uint32_t ga = 0, nacc = 0;
+    const int nchunks = Kpad / 32;
     const int frow = tid >> 1, fhalf = tid & 1;
+    bool w_ready = false;
 
     for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
         const int m0 = tile * 128;
-        int ld = 0;             // weight blocks requested for this tile (warp 0)
-        if (warp == 0) {
-            for (int i = 0; i < 2 && ld < nblk; ++i) {
-                const uint32_t slot = gl & 1;
-                if (gl >= 2) umma::mbar_wait(&b_empty[slot], ((gl - 2) >> 1) & 1);
-                umma::bulk_load(s_B + slot * 2 * LT_B, Wc + (size_t)ld * 2 * 64 * 64, 2 * LT_B, &b_full[slot]);
-                ++ld; ++gl;
-            }
-        }
-        for (int kc = 0; kc < KC; ++kc) {
+        for (int kc = 0; kc < nchunks; ++kc) {
             const uint32_t abuf = ga & 1;
             if (ga >= 2) umma::mbar_wait(&a_free[abuf], ((ga - 2) >> 1) & 1);
-            // ---- stage X[m0:m0+128, kc*64:(kc+1)*64] ----
-            {
+            {   // stage X[m0:m0+128, kc*32:(kc+1)*32]: 2 threads per row, 16 floats each
                 const int gm_row = m0 + frow;
-                const float* src = X + (size_t)(gm_row < n ? gm_row : 0) * ldx + kc * 64 + fhalf * 32;
+                const int k0 = kc * 32 + fhalf * 16;
+                const float* src = X + (size_t)(gm_row < n ? gm_row : 0) * ldx + k0;
                 unsigned char* dh = s_A + abuf * 2 * LT_A;
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int k = kc * 64 + fhalf * 32 + c4 * 4;
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int k = k0 + c4 * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (gm_row < n) {
                         if (k + 3 < ci && ((reinterpret_cast<uintptr_t>(src + c4 * 4) & 15) == 0)) v = __ldg(reinterpret_cast<const float4*>(src + c4 * 4));
@@ -77,7 +69,7 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
                     float4 h, l;
                     umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
                     umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
-                    const int kq = fhalf * 8 + c4;
+                    const int kq = fhalf * 4 + c4;
                     *reinterpret_cast<float4*>(dh + kq * (128 * 16) + frow * 16) = h;
                     *reinterpret_cast<float4*>(dh + LT_A + kq * (128 * 16) + frow * 16) = l;
                 }
@@ -85,25 +77,14 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
             umma::fence_async_smem();
             __syncthreads();
             if (warp == 0) {
+                if (!w_ready) { umma::mbar_wait(&w_full, 0); w_ready = true; }
                 umma::fence_after_sync();
                 const uint32_t a_hi = umma::smem_u32(s_A + abuf * 2 * LT_A), a_lo = a_hi + LT_A;
-                for (int nc = 0; nc < NC; ++nc) {
-                    const uint32_t slot = gm & 1;
-                    umma::mbar_wait(&b_full[slot], (gm >> 1) & 1);
-                    umma::fence_after_sync();
-                    const uint32_t b_hi = umma::smem_u32(s_B + slot * 2 * LT_B), b_lo = b_hi + LT_B;
-                    umma::issue_gemm_3xtf32(tmem + nc * 64, a_hi, a_lo, b_hi, b_lo, 64, 64, kc > 0);
-                    umma::commit(&b_empty[slot]);
-                    ++gm;
-                    if (ld < nblk) {
-                        const uint32_t s2 = gl & 1;
-                        umma::mbar_wait(&b_empty[s2], ((gl - 2) >> 1) & 1);
-                        umma::bulk_load(s_B + s2 * 2 * LT_B, Wc + (size_t)ld * 2 * 64 * 64, 2 * LT_B, &b_full[s2]);
-                        ++ld; ++gl;
-                    }
-                }
+                const uint32_t koff = (uint32_t)kc * 8 * NB * 16;     // 8 k-chunks of 4 floats, each NB*16 bytes
+                const uint32_t b_hi = umma::smem_u32(s_W) + koff, b_lo = b_hi + W_BYTES;
+                umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, 32, NB, kc > 0);
                 umma::commit(&a_free[abuf]);
-                if (kc == KC - 1) umma::commit(&acc_full);
+                if (kc == nchunks - 1) umma::commit(&acc_full);
             }
             ++ga;
         }
@@ -117,16 +98,16 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
             const int gmr = m0 + row;
             int sb = 0;
             if (seg && gmr < n) { while (sb < nseg - 1 && gmr >= __ldg(seg_off + sb)) ++sb; }
-            const int nchunk = NC * 2;   // 32-column chunks
-            for (int c = grp; c < nchunk; c += 2) {
-                if (c * 32 >= co) break;
+            for (int c = grp; c * 32 < NB; c += 2) {
+                if (grp_col0 + c * 32 >= co) break;
                 float v[32];
                 umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
                 if (gmr < n) {
+                    const int gc0 = grp_col0 + c * 32;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int gc = c * 32 + i;
-                        if (gc < co) {
+                        const int gc = gc0 + i;
+                        if (gc < co && c * 32 + i < NB) {
                             float t = v[i];
                             if (seg) t += __ldg(seg + (size_t)sb * co + gc);
                             if (scale) t *= __ldg(scale + gc);
@@ -136,12 +117,14 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
                             v[i] = t;
                         }
                     }
-                    float* dst = Y + (size_t)gmr * ldy + c * 32;
-                    if (c * 32 + 32 <= co && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    float* dst = Y + (size_t)gmr * ldy + gc0;
+                    if (gc0 + 32 <= co && c * 32 + 32 <= NB && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     } else {
-                        for (int i = 0; i < 32 && c * 32 + i < co; ++i) dst[i] = v[i];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (gc0 + i < co && c * 32 + i < NB) dst[i] = v[i];
                     }
                 }
             }
@@ -150,24 +133,35 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
         __syncthreads();   // accumulator drained before the next tile's first MMA overwrites it
         umma::fence_after_sync();
     }
+    if (warp == 0 && !w_ready) {   // CTA had no tile: still drain the weight copies before exiting
+        umma::mbar_wait(&w_full, 0);
+    }
+    __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, tcols);
 }
 
 }  // namespace
 
-// Tensor-core fused linear. Wc = [KC][NC][2][16][64][4]: 64x64 blocks of W (rows = outputs, zero padded), TF32 hi/lo split,
-// canonical K-major tiles (etch_b200/models/tc.py::tc_linear_weights); KC = ceil(ci/64), NC = ceil(co/64) <= 8.
-ETCH_API int etch_linear_tc(const float* X, int ldx, const float* Wc, int n, int ci, int co, const float* scale,
+// Tensor-core fused linear (weight-stationary).  Wc = [NG][2][Kpad/4][NB][4]: for each group of NB output columns the
+// (hi, lo) TF32 split of W[cols, :] zero-padded to Kpad = 32*ceil(ci/32), in canonical K-major tiles
+// (etch_b200/models/tc.py::tc_linear_weights chooses NB so that the tile fits shared memory).
+ETCH_API int etch_linear_tc(const float* X, int ldx, const float* Wc, int NB, int n, int ci, int co, const float* scale,
                             const float* shift, const float* R, const float* seg, const int* seg_off, int nseg, int relu,
                             float* Y, int ldy, cudaStream_t stream) {
-    if (!X || !Wc || !Y || n <= 0 || ci <= 0 || co <= 0 || co > 512) return ETCH_EINVAL;
-    const int KC = (ci + 63) / 64, NC = (co + 63) / 64;
+    if (!X || !Wc || !Y || n <= 0 || ci <= 0 || co <= 0 || NB < 16 || NB > 256 || (NB % 16)) return ETCH_EINVAL;
+    const int Kpad = ((ci + 31) / 32) * 32;
+    const int NG = (co + NB - 1) / NB;
+    const size_t wbytes = (size_t)2 * NB * Kpad * 4;
+    const size_t smem = (size_t)4 * LT_A + wbytes + 128;
+    if (smem > 227 * 1024) return ETCH_EINVAL;
     int tcols = 32;
-    while (tcols < NC * 64) tcols <<= 1;
-    const size_t smem = (size_t)4 * LT_A + (size_t)4 * LT_B + 128;
+    while (tcols < NB) tcols <<= 1;
     ETCH_TRY(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (n + 127) / 128;
-    if (grid > 148) grid = 148;
-    linear_tc_kernel<<<grid, 256, smem, stream>>>(X, ldx, Wc, n, ci, co, KC, NC, scale, shift, R, seg, seg_off, nseg, relu, Y, ldy, tcols);
+    const int ntiles = (n + 127) / 128;
+    int gx = 148 / NG;
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    dim3 grid(gx, NG);
+    linear_tc_kernel<<<grid, 256, smem, stream>>>(X, ldx, Wc, n, ci, co, Kpad, NB, scale, shift, R, seg, seg_off, nseg, relu, Y, ldy, tcols);
     ETCH_RETURN_LAST();
 }

@@ -135,6 +135,20 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
     }
 }
 
+// several bulk copies (<= 32 KB each) of one contiguous region, completing ONE phase of `bar` (warp-collective)
+__device__ __forceinline__ void bulk_load_region(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    const uint32_t d = smem_u32(dst_smem), b = smem_u32(bar);
+    if (elect_one()) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        for (uint32_t off = 0; off < bytes; off += 32768) {
+            const uint32_t nb = bytes - off < 32768 ? bytes - off : 32768;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(d + off), "l"(reinterpret_cast<const unsigned char*>(src_gmem) + off), "r"(nb), "r"(b)
+                         : "memory");
+        }
+    }
+}
+
 // fp32 -> (hi, lo) with hi = round-to-nearest tf32, lo = x - hi (exact); the tensor core truncates lo to tf32
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     uint32_t h;

@@ -214,13 +214,14 @@ def _linear(X, Wt, scale=None, shift=None, R=None, relu=False, seg=None, seg_off
     n, ci = X.shape
     co = Wt.shape[1]
     Y = torch.empty(n, co, dtype=torch.float32, device=X.device)
-    if USE_TC and ci >= 16 and 16 <= co <= 512:
+    if USE_TC and ci >= 16 and co >= 16 and ci <= 1024:
         key = (Wt.data_ptr(), tuple(Wt.shape), str(Wt.device))
-        Wc = _TC_WEIGHTS.get(key)
-        if Wc is None:
-            Wc = _TC_WEIGHTS[key] = (tc.tc_linear_weights(Wt, Wt.device), Wt)  # keep Wt alive so the pointer stays unique
-        L.call("linear_tc", L.ptr(X), ci, L.ptr(Wc[0]), n, ci, co, L.ptr(scale), L.ptr(shift), L.ptr(R), L.ptr(seg), L.ptr(seg_off),
-               0 if seg_off is None else int(seg_off.shape[0]), 1 if relu else 0, L.ptr(Y), co)
+        ent = _TC_WEIGHTS.get(key)
+        if ent is None:
+            wc, nb = tc.tc_linear_weights(Wt, Wt.device)
+            ent = _TC_WEIGHTS[key] = (wc, nb, Wt)  # keep Wt alive so the pointer stays unique
+        L.call("linear_tc", L.ptr(X), ci, L.ptr(ent[0]), ent[1], n, ci, co, L.ptr(scale), L.ptr(shift), L.ptr(R), L.ptr(seg),
+               L.ptr(seg_off), 0 if seg_off is None else int(seg_off.shape[0]), 1 if relu else 0, L.ptr(Y), co)
         return Y
     L.call("linear", L.ptr(X), ci, L.ptr(Wt), n, ci, co, L.ptr(scale), L.ptr(shift), L.ptr(R), L.ptr(seg), L.ptr(seg_off),
            0 if seg_off is None else int(seg_off.shape[0]), 1 if relu else 0, L.ptr(Y), co)

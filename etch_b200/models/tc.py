@@ -32,12 +32,17 @@ def tc_operand_chunks(w_nk, kchunk, device):
     return torch.stack([tc_operand(w_nk[:, c:c + kchunk], "cpu") for c in range(0, k, kchunk)], 0).contiguous().to(device)
 
 
-def tc_linear_weights(wt_ci_co, device):
-    """Wt [ci, co] (the transposed nn.Linear weight used by etch_linear) -> [KC, NC, 2, 16, 64, 4] blocks for etch_linear_tc."""
+def tc_linear_weights(wt_ci_co, device, smem_budget=150 * 1024):
+    """Wt [ci, co] (the transposed nn.Linear weight used by etch_linear) -> (Wc [NG, 2, Kpad/4, NB, 4], NB) for
+    etch_linear_tc: groups of NB output columns whose (hi, lo) tile fits `smem_budget` bytes of shared memory."""
     w = wt_ci_co.detach().float().cpu().t().contiguous()  # [co, ci]
     co, ci = w.shape
-    KC, NC = (ci + 63) // 64, (co + 63) // 64
-    wp = torch.zeros(NC * 64, KC * 64)
+    kpad = ((ci + 31) // 32) * 32
+    nb = min(256, ((co + 15) // 16) * 16, (smem_budget // (8 * kpad)) // 16 * 16)
+    if nb < 16:
+        raise ValueError("layer too wide for the weight-stationary kernel: ci=%d" % ci)
+    ng = (co + nb - 1) // nb
+    wp = torch.zeros(ng * nb, kpad)
     wp[:co, :ci] = w
-    blocks = [[tc_operand(wp[nc * 64:(nc + 1) * 64, kc * 64:(kc + 1) * 64], "cpu") for nc in range(NC)] for kc in range(KC)]
-    return torch.stack([torch.stack(b, 0) for b in blocks], 0).contiguous().to(device)
+    groups = [tc_operand(wp[g * nb:(g + 1) * nb], "cpu") for g in range(ng)]   # each [2, kpad/4, nb, 4]
+    return torch.stack(groups, 0).contiguous().to(device), nb
