@@ -174,6 +174,185 @@ __global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
     if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// InterSO3Conv with the channel-mixing GEMM on the tensor cores.
+//   z[(p,a), o] = sum_{c,k} W[o, c*24+k] * ( sum_n f[nbr(p,n), a, c] * relu(1 - |g_n - R_a kappa_k|^2 / sigma) ) + bias[o]
+// (vgtk/so3conv/functional.py:286-324,61-67; modules.py:19-39,120-128).  The neighbour contraction (150k tiny
+// block-diagonal products per scan: not a dense GEMM) stays on the CUDA cores exactly as in inter_conv_kernel; its
+// result y is produced in slabs of 8 channels x 12 kernel points = 96 K-columns for all 120 (p,a) rows, written straight
+// into the canonical UMMA A tile as (hi, lo) TF32 pairs, and multiplied with the matching pre-split slab of W by
+// tcgen05.mma (3xTF32) while the CUDA cores already work on the next slab.  Weight slabs stream through a 2-deep
+// cp.async.bulk ring; the [128 x C_out] accumulator lives in TMEM for the whole tile.
+template <int CIN, int COUT, int NN>
+__global__ void __launch_bounds__(256, 1) inter_conv_tc_kernel(
+    const float* __restrict__ xyz,       // [B,3,q]
+    const float* __restrict__ feat,      // [B,q,60,CIN]
+    const int* __restrict__ sample_idx,  // [B,P]
+    const int* __restrict__ nbr,         // [B,P,NN]
+    const float4* __restrict__ krs,      // [60,24] {2/sigma * R_a k, |R_a k|^2/sigma}
+    const float* __restrict__ Wc,        // [CIN/8*2][2][24][COUT][4]  weight slabs (hi, lo), K'' = kgl*48 + c*6 + i
+    const float* __restrict__ bias,
+    int q, int P, float inv_sigma,
+    float* __restrict__ zraw, double* __restrict__ stats)
+{
+    constexpr int NK = 24;
+    constexpr int KS = 96;                            // K columns per slab
+    constexpr int NSLAB = CIN / 8 * 2;
+    constexpr uint32_t A_BYTES = MROWS * KS * 4;      // 49152
+    constexpr uint32_t W_BYTES = COUT * KS * 4;       // one (hi|lo) weight slab
+    constexpr int TCOLS = COUT < 32 ? 32 : COUT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* s_A = smem_raw;                                        // [hi | lo]
+    unsigned char* s_W = s_A + 2 * A_BYTES;                               // [2 slots][hi | lo]
+    float4* s_krs = reinterpret_cast<float4*>(s_W + 4 * W_BYTES);         // [60*24]
+    float4* s_g = s_krs + NA * NK;                                        // [TP][NN]
+    int* s_off = reinterpret_cast<int*>(s_g + TP * NN);                   // [TP][NN]
+    float* s_z = reinterpret_cast<float*>(s_A);                           // epilogue reuse [128][COUT]
+    __shared__ uint64_t bar_mma, bar_w[2];
+    __shared__ uint32_t tmem_base;
+
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < NA * NK; i += 256) s_krs[i] = __ldg(krs + i);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, TCOLS);
+    if (tid == 0) { umma::mbar_init(&bar_mma, 1); umma::mbar_init(&bar_w[0], 1); umma::mbar_init(&bar_w[1], 1); }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = umma::uniform(tmem_base);
+    const float* X = xyz + (size_t)b * 3 * q;
+    const float* F = feat + (size_t)b * q * NA * CIN;
+    uint32_t n_mma = 0, n_w = 0;     // MMA groups issued / weight slabs requested so far (uniform)
+    double acc_s = 0.0, acc_ss = 0.0;
+    const int ntiles = (P + TP - 1) / TP;
+    // GEMM1 task of this thread: pair = 16*warp + lane%16 (valid < 120), kernel-point half kgl = lane/16
+    const int pair = warp * 16 + (lane & 15), kgl = lane >> 4;
+    const bool task_ok = pair < NPAIR;
+    const int pl = task_ok ? pair / NA : 0, a = task_ok ? pair % NA : 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * TP;
+        const int npts = min(TP, P - p0);
+        if (warp == 0) { umma::bulk_load(s_W + (n_w & 1) * 2 * W_BYTES, Wc, 2 * W_BYTES, &bar_w[n_w & 1]); }
+        ++n_w;
+        for (int t = tid; t < TP * NN; t += 256) {
+            const int ppl = t / NN, n = t % NN;
+            const int p = min(p0 + ppl, P - 1);
+            const int c = __ldg(sample_idx + (size_t)b * P + p);
+            const int k = __ldg(nbr + ((size_t)b * P + p) * NN + n);
+            const float gx = __ldg(X + k) - __ldg(X + c);
+            const float gy = __ldg(X + q + k) - __ldg(X + q + c);
+            const float gz = __ldg(X + 2 * (size_t)q + k) - __ldg(X + 2 * (size_t)q + c);
+            s_g[t] = make_float4(gx, gy, gz, 1.0f - (gx * gx + gy * gy + gz * gz) * inv_sigma);
+            s_off[t] = k * NA * CIN;
+        }
+        for (int t = tid; t < (MROWS - NPAIR) * (KS / 4) * 2; t += 256) {   // pad rows of the A tile (aliased by s_z)
+            const int which = t / ((MROWS - NPAIR) * (KS / 4)), rem = t % ((MROWS - NPAIR) * (KS / 4));
+            const int r = NPAIR + rem / (KS / 4), kc = rem % (KS / 4);
+            *reinterpret_cast<float4*>(s_A + which * A_BYTES + kc * (MROWS * 16) + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        for (int sl = 0; sl < NSLAB; ++sl) {
+            const int c0 = (sl >> 1) * 8, kg = (sl & 1) * 2 + kgl;
+            // ---- GEMM1 for this slab: y[c][i] = sum_n f[nbr_n][a][c0+c] * w[a][kg*6+i][n] ----
+            float acc[8][6];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc[c][i] = 0.f;
+            if (task_ok) {
+                float4 kq[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) kq[i] = s_krs[a * NK + kg * 6 + i];
+                const float* fa = F + a * CIN + c0;
+                float4 f0 = __ldg(reinterpret_cast<const float4*>(fa + s_off[pl * NN]));
+                float4 f1 = __ldg(reinterpret_cast<const float4*>(fa + s_off[pl * NN]) + 1);
+#pragma unroll 2
+                for (int n = 0; n < NN; ++n) {
+                    const float4 g = s_g[pl * NN + n];
+                    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                    if (n + 1 < NN) {
+                        const float4* fp = reinterpret_cast<const float4*>(fa + s_off[pl * NN + n + 1]);
+                        f0 = __ldg(fp); f1 = __ldg(fp + 1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const float w = fmaxf(fmaf(g.x, kq[i].x, fmaf(g.y, kq[i].y, fmaf(g.z, kq[i].z, g.w - kq[i].w))), 0.f);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[c][i] = fmaf(fv[c], w, acc[c][i]);
+                    }
+                }
+            }
+            // ---- the previous slab's MMAs must have finished reading the A tile; then request the next weight slab ----
+            if (n_mma > 0) { umma::mbar_wait(&bar_mma, (n_mma - 1) & 1); umma::fence_after_sync(); }
+            if (warp == 0 && sl + 1 < NSLAB) {
+                umma::bulk_load(s_W + (n_w & 1) * 2 * W_BYTES, Wc + (size_t)(sl + 1) * 2 * COUT * KS, 2 * W_BYTES, &bar_w[n_w & 1]);
+            }
+            if (sl + 1 < NSLAB) ++n_w;
+            // ---- y -> canonical A tile as (hi, lo): 48 consecutive K columns of this row = 12 float4 each ----
+            if (task_ok) {
+                const float* av = &acc[0][0];   // v = c*6 + i
+#pragma unroll
+                for (int v4 = 0; v4 < 12; ++v4) {
+                    float4 h, l;
+                    umma::split_tf32(av[v4 * 4 + 0], h.x, l.x); umma::split_tf32(av[v4 * 4 + 1], h.y, l.y);
+                    umma::split_tf32(av[v4 * 4 + 2], h.z, l.z); umma::split_tf32(av[v4 * 4 + 3], h.w, l.w);
+                    const int kc = kgl * 12 + v4;
+                    *reinterpret_cast<float4*>(s_A + kc * (MROWS * 16) + pair * 16) = h;
+                    *reinterpret_cast<float4*>(s_A + A_BYTES + kc * (MROWS * 16) + pair * 16) = l;
+                }
+            }
+            umma::fence_async_smem();
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t gw = n_w - (sl + 1 < NSLAB ? 2 : 1);      // index of the weight slab consumed now
+                umma::mbar_wait(&bar_w[gw & 1], (gw >> 1) & 1);
+                umma::fence_after_sync();
+                const uint32_t a_hi = umma::smem_u32(s_A), a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = umma::smem_u32(s_W + (gw & 1) * 2 * W_BYTES), b_lo = b_hi + W_BYTES;
+                umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, KS, COUT, sl > 0);
+                umma::commit(&bar_mma);
+            }
+            ++n_mma;
+        }
+        // ---- epilogue ----
+        umma::mbar_wait(&bar_mma, (n_mma - 1) & 1);
+        umma::fence_after_sync();
+        {
+            const int qq = warp & 3, half = warp >> 2;
+            const int row = qq * 32 + lane;
+#pragma unroll
+            for (int cc = 0; cc < COUT / 2; cc += 8) {
+                float v[8];
+                const int col = half * (COUT / 2) + cc;
+                umma::tmem_ld8(tmem + ((uint32_t)(qq * 32) << 16) + col, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s_z[row * COUT + col + i] = v[i] + __ldg(bias + col + i);
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        const int nvalid = npts * NA;
+        float* dst = zraw + ((size_t)b * P + p0) * NA * COUT;
+        for (int i = tid; i < nvalid * COUT / 4; i += 256)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_z)[i];
+        if (tid < COUT) {
+            float s = 0.f, ss = 0.f;
+            for (int r = 0; r < nvalid; ++r) { const float v = s_z[r * COUT + tid]; s += v; ss = fmaf(v, v, ss); }
+            acc_s += (double)s; acc_ss += (double)ss;
+        }
+        __syncthreads();
+    }
+    if (tid < COUT) {
+        atomicAdd(stats + ((size_t)b * COUT + tid) * 2, acc_s);
+        atomicAdd(stats + ((size_t)b * COUT + tid) * 2 + 1, acc_ss);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+}
+
 int grid_for_tc(int ntiles, int B) {
     int g = 148 / B;   // one wave of persistent CTAs (1 CTA/SM)
     if (g < 1) g = 1;
@@ -193,7 +372,33 @@ int launch_agemm_tc(const float* xin, const int* src_idx, const int* tab, const 
     ETCH_RETURN_LAST();
 }
 
+template <int CIN, int COUT, int NN>
+int launch_inter_tc(const float* xyz, const float* feat, const int* sample_idx, const int* nbr, const float* krs, const float* Wc,
+                    const float* bias, int B, int q, int P, float sigma, float* zraw, double* stats, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)2 * MROWS * 96 * 4 + (size_t)4 * COUT * 96 * 4 + (size_t)NA * 24 * 16 + (size_t)TP * NN * 16 +
+                            (size_t)TP * NN * 4 + 128;
+    auto kern = inter_conv_tc_kernel<CIN, COUT, NN>;
+    ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(grid_for_tc((P + TP - 1) / TP, B), B);
+    kern<<<grid, 256, smem, stream>>>(xyz, feat, sample_idx, nbr, reinterpret_cast<const float4*>(krs), Wc, bias, q, P, 1.0f / sigma,
+                                      zraw, stats);
+    ETCH_RETURN_LAST();
+}
+
 }  // namespace
+
+// Tensor-core InterSO3Conv (c_in in {32,64}).  Wc = [cin/8*2][2][24][cout][4]: weight slabs in (hi, lo) canonical tiles with
+// K'' = kgl*48 + c*6 + i  <->  W[o][(c0+c)*24 + (2h+kgl)*6 + i]  (etch_b200/models/encoder.py).
+ETCH_API int etch_so3_inter_conv_tc(const float* xyz, const float* feat, const int* sample_idx, const int* nbr, const float* krs,
+                                    const float* Wc, const float* bias, int B, int q, int P, int nn, int cin, int cout,
+                                    float sigma, float* zraw, double* stats, cudaStream_t stream) {
+    if (!xyz || !feat || !sample_idx || !nbr || !krs || !Wc || !bias || !zraw || !stats) return ETCH_EINVAL;
+#define CASE(ci, co, n) \
+    if (cin == ci && cout == co && nn == n) return launch_inter_tc<ci, co, n>(xyz, feat, sample_idx, nbr, krs, Wc, bias, B, q, P, sigma, zraw, stats, stream);
+    CASE(32, 32, 32) CASE(32, 64, 64) CASE(64, 64, 32)
+#undef CASE
+    return ETCH_EINVAL;
+}
 
 // Tensor-core IntraSO3Conv. Wc = [12][2][c/4][cout][4] (TF32 hi/lo split, canonical K-major tiles; see etch_b200/models/tc.py)
 ETCH_API int etch_so3_intra_conv_tc(const float* zin, const double* in_stats, const int* intra_idx, const float* Wc,

@@ -21,6 +21,18 @@ def to_reference_layout(feats_bpac):
     return feats_bpac.permute(0, 3, 1, 2).contiguous()
 
 
+def _inter_slabs(W, ci, co):
+    """BasicSO3Conv weight [co, ci*24] -> [ci/8*2, 2, 24, co, 4]: per (8-channel chunk, kernel-point half) the [co x 96] slab in
+    the column order K'' = kgl*48 + c*6 + i used by inter_conv_tc_kernel, TF32 hi/lo split, canonical tiles."""
+    W3 = W.view(co, ci, 24)
+    slabs = []
+    for sl in range(ci // 8 * 2):
+        c0, h = (sl // 2) * 8, sl % 2
+        blk = W3[:, c0:c0 + 8, h * 12:(h + 1) * 12].reshape(co, 8, 2, 6).permute(0, 2, 1, 3).reshape(co, 96)  # [o][kgl][c][i]
+        slabs.append(tc.tc_operand(blk.contiguous(), "cpu"))
+    return torch.stack(slabs, 0).contiguous()
+
+
 class EncoderPlan:
     """Device-resident, kernel-friendly copies of the encoder weights (built once per state_dict/device)."""
 
@@ -50,6 +62,7 @@ class EncoderPlan:
                 Wt_skip=sd[pre + "skip_conv.weight"].to(**f32).view(co, ci).t().contiguous(),  # [c][o]
                 # tensor-core operands: per anchor-neighbour slot j the [c_out x c] slice, TF32-split, canonical tiles
                 Wc_intra=torch.stack([tc.tc_operand(Wi.view(co, co, 12)[:, :, j].cpu(), "cpu") for j in range(12)], 0).contiguous().to(device),
+                Wc_inter=(_inter_slabs(W.cpu(), ci, co).to(device) if ci > 1 else None),
                 Wc_skip=(tc.tc_operand(sd[pre + "skip_conv.weight"].view(co, ci).cpu(), device)[None].contiguous() if ci > 1 else None),
                 b_skip=sd[pre + "skip_conv.bias"].to(**f32).contiguous(),
             )
@@ -84,9 +97,9 @@ def run_encoder(plan, xyz_bcn, trace=None):
             L.call("so3_inter_conv_c1", L.ptr(xyz), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["kr"]), L.ptr(lp["Wt_inter"]),
                    L.ptr(lp["b_inter"]), B, q, P, nn_, co, L.f32(lp["sigma"]), L.ptr(z1), L.ptr(stats[0]))
         else:
-            L.call("so3_inter_conv", L.ptr(xyz), L.ptr(feats), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["krs"]),
-                   L.ptr(lp["Wt_inter"]), L.ptr(lp["b_inter"]), B, q, P, nn_, ci, co, L.f32(lp["sigma"]), L.ptr(z1),
-                   L.ptr(stats[0]))
+            L.call("so3_inter_conv_tc" if USE_TC else "so3_inter_conv", L.ptr(xyz), L.ptr(feats), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["krs"]),
+                   L.ptr(lp["Wc_inter"] if USE_TC else lp["Wt_inter"]), L.ptr(lp["b_inter"]), B, q, P, nn_, ci, co, L.f32(lp["sigma"]),
+                   L.ptr(z1), L.ptr(stats[0]))
         z2 = torch.empty_like(z1)
         if USE_TC:
             L.call("so3_intra_conv_tc", L.ptr(z1), L.ptr(stats[0]), L.ptr(lp["intra_idx"]), L.ptr(lp["Wc_intra"]),
