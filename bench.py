@@ -167,12 +167,13 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------------- etch arm
 class Pipeline:
-    """the public operator API of the repo, as a caller of the reference's eval.py would use it."""
+    """the public operator API of the repo: GT_network_equiv + the fit, driven through etch_b200.runtime.ScanFitter
+    (CUDA-graph replay of the exact kernel sequence the eager API launches)."""
 
-    def __init__(self, device):
+    def __init__(self, device, use_graph=True):
         from etch_b200 import smpl_model, synth
-        from etch_b200.models import fit_SMPL
         from etch_b200.models.models_pointcloud import GT_network_equiv
+        from etch_b200.runtime import ScanFitter
         self.ms = _markerset()
         opt = types.SimpleNamespace(output_folder=None, EPN_input_radius=0.4, EPN_layer_num=2, markerset=self.ms)
         import contextlib
@@ -182,14 +183,15 @@ class Pipeline:
         self.net.load_state_dict(synth.make_state_dict(1))
         self.net = self.net.to(device).eval()
         self.args = types.SimpleNamespace(markerset=self.ms, smpl_model=smpl_model.synthetic_body(0), device=str(device))
-        self.fit = fit_SMPL
-        self.tables = fit_SMPL.body_tables(self.args, "neutral", device)
+        self.device = device
+        self.fitter = ScanFitter(self.net, self.args, "neutral", use_graph=use_graph)
+        self.eager = ScanFitter(self.net, self.args, "neutral", use_graph=False)
 
     def step(self, pts):
-        out, _ = self.net(pts, ["confidence", "direction", "magnitude"], "standard_vector")
-        labels, vec, inner = self.net.postprocess(pts, out)
-        markers, valid = self.fit.get_markers(self.args, inner, labels, out["confidences"])
-        return self.fit.lm_fit(self.tables, markers, valid)
+        return self.fitter(pts)
+
+    def step_from_host(self, pinned):
+        return self.fitter(pinned, device=self.device)
 
 
 def run_etch(args, rank, world, local_rank):
@@ -203,7 +205,7 @@ def run_etch(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     B, N = args.batch, args.points
-    pipe = Pipeline(device)
+    pipe = Pipeline(device, use_graph=not args.no_graph)
     n_pool = 4
     host = [torch.from_numpy(synth.sample_scans(B, N, 50 + rank * 100 + i)).pin_memory() for i in range(n_pool)]
     dev_in = [h.to(device) for h in host]
@@ -229,7 +231,8 @@ def run_etch(args, rank, world, local_rank):
         pipe.step(dev_in[i % n_pool])
         ev[i][1].record()
     barrier()
-    launches = (_lib.launch_count - l0)
+    # kernels launched in the timed region: counted at the C-ABI when eager, = captured kernel nodes x replays with the graph
+    launches = (_lib.launch_count - l0) if args.no_graph else pipe.fitter.launches_per_step * args.steps
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([float(sum(step_ms))], device=device)
     sharding.max_over_ranks(total_ms)
@@ -242,8 +245,7 @@ def run_etch(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        pts = host[i % n_pool].to(device, non_blocking=True)
-        fit = pipe.step(pts)
+        fit = pipe.step_from_host(host[i % n_pool])
         out_v.copy_(fit["vertices"], non_blocking=True)
         out_p.copy_(fit["params"], non_blocking=True)
         out_j.copy_(fit["joints"], non_blocking=True)
@@ -257,7 +259,7 @@ def run_etch(args, rank, world, local_rank):
     prof = None
     if rank == 0:
         _lib.start_profile()
-        pipe.step(dev_in[0])
+        pipe.eager(dev_in[0])
         prof = _lib.stop_profile()
     barrier()
     if rank != 0:
@@ -300,7 +302,8 @@ def run_etch(args, rank, world, local_rank):
             "config": {"workload": "5k-pt clothed scans, batch 8 per GPU, full net forward + 2-stage LM SMPL fit (BASELINE configs[1])",
                        "points": N, "batch_per_gpu": B, "global_batch": scans, "parallelism": "scan-sharded x%d (no data-path collective)" % world,
                        "weights": "seeded random init, reference state-dict layout", "body_model": "synthetic SMPL-shaped (6890 verts)",
-                       "l2": "256 MiB flush write between timed steps (not timed)"},
+                       "l2": "256 MiB flush write between timed steps (not timed)",
+                       "launch": "eager" if args.no_graph else "CUDA graph replay of the step (etch_b200.runtime.ScanFitter)"},
             "e2e": {"value": scans / (e2e_ms_step * 1e-3), "unit": "scans/s", "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": B * (6890 * 3 + 85 + 45 * 3) * 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels_ms": kernels}
@@ -316,6 +319,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--points", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

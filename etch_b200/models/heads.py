@@ -173,11 +173,21 @@ class PTGeometry:
     """Point hierarchy + the 13 neighbour graphs of one batch (shared by both PointTransformers: FPS and kNN depend
     only on the coordinates).  The reference recomputes them 88 times per forward (pointtransformer_seg.py:28-29,59-61,95)."""
 
+    _OFFSETS = {}   # (sizes, device) -> cumulative-offset tensor, built once (no H2D copies inside a CUDA-graph capture)
+
+    @classmethod
+    def _offsets(cls, sizes, dev):
+        key = (tuple(sizes), str(dev))
+        t = cls._OFFSETS.get(key)
+        if t is None:
+            t = cls._OFFSETS[key] = torch.tensor([sum(sizes[:i + 1]) for i in range(len(sizes))], dtype=torch.int32, device=dev)
+        return t
+
     def __init__(self, p0, B, N):
         dev = p0.device
         self.p, self.off, self.n = [p0], [], []
         sizes = [N] * B
-        off = torch.tensor([sum(sizes[:i + 1]) for i in range(B)], dtype=torch.int32, device=dev)
+        off = self._offsets(sizes, dev)
         self.off.append(off)
         self.n.append(sum(sizes))
         self.seg = [sizes]
@@ -187,7 +197,7 @@ class PTGeometry:
                 prev_p, prev_off, prev_sizes = self.p[lvl - 1], self.off[lvl - 1], self.seg[lvl - 1]
                 sizes = [s // PT_STRIDE[lvl] for s in prev_sizes]
                 m = sum(sizes)
-                off = torch.tensor([sum(sizes[:i + 1]) for i in range(B)], dtype=torch.int32, device=dev)
+                off = self._offsets(sizes, dev)
                 idx = torch.empty(m, dtype=torch.int32, device=dev)
                 L.call("fps_packed", B, max(prev_sizes), L.ptr(prev_p), L.ptr(prev_off), L.ptr(off), L.ptr(None), L.ptr(idx))
                 newp = torch.empty(m, 3, dtype=torch.float32, device=dev)

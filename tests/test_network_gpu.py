@@ -145,3 +145,28 @@ def test_full_size_forward_properties(cuda):
     # InstanceNorm statistics use double atomics (order-dependent in the last bits): runs agree to fp32 noise
     assert _rel(o1["part_labels"], o0["part_labels"]) < 1e-4
     assert o0["part_labels"].shape == (8, 5000, 86)
+
+
+def test_scan_fitter_graph_replay_matches_eager(cuda):
+    """CUDA-graph replay of the whole step (etch_b200.runtime.ScanFitter) == the eager kernel sequence, for device and
+    pinned-host inputs, across repeated calls with different scans."""
+    from etch_b200 import smpl_model, synth
+    from etch_b200.runtime import ScanFitter
+    net, _ = _model(cuda)
+    ms = json.load(open(os.path.join(ROOT, "etch_b200", "data", "superset_smpl.json")))
+    args = types.SimpleNamespace(markerset=ms, smpl_model=smpl_model.synthetic_body(0), device="cuda:0")
+    eager = ScanFitter(net, args, use_graph=False)
+    graphed = ScanFitter(net, args, use_graph=True)
+    for seed in (1, 2):
+        pts = torch.from_numpy(synth.sample_scans(2, 1024, seed))
+        ref = {k: v.clone() for k, v in eager(pts.to(cuda)).items()}
+        out = graphed(pts.to(cuda))
+        torch.cuda.synchronize()
+        assert (out["labels"] == ref["labels"]).all()
+        assert (out["valid"] == ref["valid"]).all()
+        v2v = (out["vertices"] - ref["vertices"]).norm(dim=-1).mean().item() * 1000.0
+        assert v2v < 0.05, v2v   # mm; only the double-atomic InstanceNorm statistics are order dependent
+        out2 = graphed(pts.pin_memory(), device=cuda)
+        torch.cuda.synchronize()
+        assert (out2["vertices"] - ref["vertices"]).norm(dim=-1).mean().item() * 1000.0 < 0.05
+    assert graphed.launches_per_step > 500

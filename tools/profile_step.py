@@ -11,7 +11,7 @@ from etch_b200 import synth  # noqa: E402
 B = int(os.environ.get("ETCH_PROFILE_BATCH", "8"))
 N = int(os.environ.get("ETCH_PROFILE_POINTS", "5000"))
 dev = torch.device("cuda:0")
-pipe = bench.Pipeline(dev)
+pipe = bench.Pipeline(dev, use_graph=False)
 pts = torch.from_numpy(synth.sample_scans(B, N, 50)).to(dev)
 for _ in range(2):
     pipe.step(pts)
