@@ -14,25 +14,26 @@
 
 namespace {
 
-constexpr int CT_N = 32;    // weight columns (GEMM N) per chunk
+constexpr int CT_N = 128;   // weight rows per marker group (GEMM N)
+constexpr int CT_KQ = 32;   // K columns per streamed slice (a group = 4 slices)
 constexpr int CT_K = 128;   // feature dimension
 
 __global__ void __launch_bounds__(256, 1) conf_head_tc_kernel(const float* __restrict__ x,       // [n][128]
                                                               const float* __restrict__ logits,  // [n][K]
-                                                              const float* __restrict__ W0c,     // [K*4][2][32][32][4]
+                                                              const float* __restrict__ W0c,     // [K*4][2][8][128][4]
                                                               const float* __restrict__ b0,      // [K*128]
                                                               const float* __restrict__ w2,      // [K][128]
                                                               const float* __restrict__ b2,      // [K]
                                                               int n, int K, float* __restrict__ conf) {
     constexpr uint32_t A_BYTES = 128 * CT_K * 4;      // 64 KB per (hi|lo)
-    constexpr uint32_t B_BYTES = CT_N * CT_K * 4;     // 16 KB per (hi|lo)
+    constexpr uint32_t B_BYTES = CT_N * CT_KQ * 4;    // 16 KB per (hi|lo) slice [128 rows x 32 k]
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* s_A = smem_raw;                    // [hi | lo]
     unsigned char* s_B = s_A + 2 * A_BYTES;           // [2 buffers][hi | lo]
     __shared__ uint64_t b_full[2], b_empty[2], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) umma::tmem_alloc(&tmem_base, 64);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&b_full[i], 1); umma::mbar_init(&b_empty[i], 1);
@@ -43,13 +44,13 @@ __global__ void __launch_bounds__(256, 1) conf_head_tc_kernel(const float* __res
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = umma::uniform(tmem_base);
-    const int nchunk = K * 4;
-    uint32_t gi = 0;  // global chunk counter (barrier phases run across tiles)
+    const int nslice = K * 4;
+    uint32_t gs = 0;  // global slice counter, gg = global group counter (barrier phases run across tiles)
+    uint32_t gg = 0;
 
     for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
         const int m0 = tile * 128;
-        // ---- fill the A tile: 2 threads per row, TF32 split, canonical layout ----
-        {
+        {   // A tile: 2 threads per row, TF32 split, canonical layout
             const int r = tid >> 1, half = tid & 1;
             const bool ok = m0 + r < n;
             const float4* src = reinterpret_cast<const float4*>(x + (size_t)(ok ? m0 + r : 0) * CT_K + half * 64);
@@ -68,30 +69,33 @@ __global__ void __launch_bounds__(256, 1) conf_head_tc_kernel(const float* __res
         __syncthreads();
 
         if (warp == 0) {
-            // ===== weight streaming + MMA issue (warp-collective, one elected lane executes) =====
+            // ===== weight streaming + MMA issue (warp-collective) =====
             const uint32_t a_hi = umma::smem_u32(s_A), a_lo = a_hi + A_BYTES;
-            {   // first slice of the tile: its buffer was last read by MMA (gi-2), which completed before the tile barrier
-                const uint32_t g = gi;
+            {
+                const uint32_t g = gs;
                 if (g >= 2) umma::mbar_wait(&b_empty[g & 1], ((g - 2) >> 1) & 1);
                 umma::bulk_load(s_B + (g & 1) * 2 * B_BYTES, W0c, 2 * B_BYTES, &b_full[g & 1]);
             }
-            for (int i = 0; i < nchunk; ++i) {
-                const uint32_t g = gi + i, buf = g & 1;
-                if (i + 1 < nchunk) {
+            for (int i = 0; i < nslice; ++i) {
+                const uint32_t g = gs + i, buf = g & 1;
+                const int kq = i & 3;
+                const uint32_t grp = gg + (i >> 2), acc = grp & 1;
+                if (i + 1 < nslice) {
                     const uint32_t g1 = g + 1, nb = g1 & 1;
                     if (g1 >= 2) umma::mbar_wait(&b_empty[nb], ((g1 - 2) >> 1) & 1);
-                    umma::bulk_load(s_B + nb * 2 * B_BYTES, W0c + (size_t)(i + 1) * 2 * CT_N * CT_K, 2 * B_BYTES, &b_full[nb]);
+                    umma::bulk_load(s_B + nb * 2 * B_BYTES, W0c + (size_t)(i + 1) * 2 * CT_N * CT_KQ, 2 * B_BYTES, &b_full[nb]);
                 }
                 umma::mbar_wait(&b_full[buf], (g >> 1) & 1);
-                if (g >= 2) umma::mbar_wait(&t_empty[buf], ((g - 2) >> 1) & 1);
+                if (kq == 0 && grp >= 2) umma::mbar_wait(&t_empty[acc], ((grp - 2) >> 1) & 1);
                 umma::fence_after_sync();
                 const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
-                umma::issue_gemm_3xtf32(tmem + buf * CT_N, a_hi, a_lo, b_hi, b_lo, CT_K, CT_N, false);
+                // K quarter kq of the canonical A tile starts 8 k-chunks (8 * 2048 bytes) further per quarter
+                umma::issue_gemm_3xtf32(tmem + acc * CT_N, a_hi + kq * 8 * 2048, a_lo + kq * 8 * 2048, b_hi, b_lo, CT_KQ, CT_N, kq > 0);
                 umma::commit(&b_empty[buf]);
-                umma::commit(&t_full[buf]);
+                if (kq == 3) umma::commit(&t_full[acc]);
             }
         } else if (warp >= 4) {
-            // ===== epilogue: one thread per point =====
+            // ===== epilogue: one thread per point, one marker group (128 columns) per accumulator =====
             const int q = warp & 3;
             const int row = q * 32 + lane;
             const int m = m0 + row;
@@ -102,49 +106,51 @@ __global__ void __launch_bounds__(256, 1) conf_head_tc_kernel(const float* __res
             float den = 0.f;
             for (int l = 0; l < K; ++l) den += expf(__ldg(lr + l) - mx);
             const float inv_den = 1.0f / den;
-            float acc_conf = 0.f, part = 0.f;
-            for (int i = 0; i < nchunk; ++i) {
-                const uint32_t g = gi + i, buf = g & 1;
-                umma::mbar_wait(&t_full[buf], (g >> 1) & 1);
+            float acc_conf = 0.f;
+            for (int l = 0; l < K; ++l) {
+                const uint32_t grp = gg + l, acc = grp & 1;
+                umma::mbar_wait(&t_full[acc], (grp >> 1) & 1);
                 umma::fence_after_sync();
-                float v[32];
-                umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * CT_N, v);
-                umma::fence_before_sync();
-                umma::mbar_arrive(&t_empty[buf]);
-                const float4* bp = reinterpret_cast<const float4*>(b0 + (size_t)i * CT_N);
-                const float4* wp = reinterpret_cast<const float4*>(w2 + (size_t)i * CT_N);
+                float part = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < CT_N; c0 += 32) {
+                    float v[32];
+                    umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * CT_N + c0, v);
+                    const float4* bp = reinterpret_cast<const float4*>(b0 + (size_t)l * CT_N + c0);
+                    const float4* wp = reinterpret_cast<const float4*>(w2 + (size_t)l * CT_N + c0);
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 bb = __ldg(bp + j4), ww = __ldg(wp + j4);
-                    part = fmaf(fmaxf(v[j4 * 4 + 0] + bb.x, 0.f), ww.x, part);
-                    part = fmaf(fmaxf(v[j4 * 4 + 1] + bb.y, 0.f), ww.y, part);
-                    part = fmaf(fmaxf(v[j4 * 4 + 2] + bb.z, 0.f), ww.z, part);
-                    part = fmaf(fmaxf(v[j4 * 4 + 3] + bb.w, 0.f), ww.w, part);
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bb = __ldg(bp + j4), ww = __ldg(wp + j4);
+                        part = fmaf(fmaxf(v[j4 * 4 + 0] + bb.x, 0.f), ww.x, part);
+                        part = fmaf(fmaxf(v[j4 * 4 + 1] + bb.y, 0.f), ww.y, part);
+                        part = fmaf(fmaxf(v[j4 * 4 + 2] + bb.z, 0.f), ww.z, part);
+                        part = fmaf(fmaxf(v[j4 * 4 + 3] + bb.w, 0.f), ww.w, part);
+                    }
                 }
-                if ((i & 3) == 3) {  // marker group finished
-                    const int l = i >> 2;
-                    const float p = expf(__ldg(lr + l) - mx) * inv_den;
-                    acc_conf = fmaf(p, part + __ldg(b2 + l), acc_conf);
-                    part = 0.f;
-                }
+                umma::fence_before_sync();
+                umma::mbar_arrive(&t_empty[acc]);
+                const float p = expf(__ldg(lr + l) - mx) * inv_den;
+                acc_conf = fmaf(p, part + __ldg(b2 + l), acc_conf);
             }
             if (ok) conf[m] = acc_conf;
         }
-        gi += nchunk;
+        gs += nslice;
+        gg += K;
         umma::fence_before_sync();
         __syncthreads();   // A tile and accumulators are free for the next tile
         umma::fence_after_sync();
     }
-    if (warp == 0) umma::tmem_dealloc(tmem, 64);
+    if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace
 
-// Tensor-core confidence head. W0c = [K*4][2][32][32][4]: per 32-column slice of confi.0's weight, (hi, lo) canonical tiles.
+// Tensor-core confidence head. W0c = [K*4][2][8][128][4]: per marker group l and K-quarter kq the [128 rows x 32 k] slice of
+// confi.0's weight as (hi, lo) canonical tiles (etch_b200/models/heads.py).
 ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float* W0c, const float* b0, const float* w2,
                                const float* b2, int n, int K, float* conf, cudaStream_t stream) {
     if (!x || !logits || !W0c || !b0 || !w2 || !b2 || !conf || n <= 0 || K <= 0) return ETCH_EINVAL;
-    const size_t smem = (size_t)2 * 128 * CT_K * 4 + (size_t)4 * CT_N * CT_K * 4 + 128;
+    const size_t smem = (size_t)2 * 128 * CT_K * 4 + (size_t)4 * CT_N * CT_KQ * 4 + 128;
     ETCH_TRY(cudaFuncSetAttribute(conf_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = etch_cdiv(n, 128);
     if (grid > 148) grid = 148;

@@ -75,6 +75,7 @@ __device__ __forceinline__ void fps_segment(const FpsSeg& s, int T_ref, float* s
             if (k < s.n) { sx[k] = x; sy[k] = y; }
         } else {
             px[i] = x; py[i] = y;
+            if (k < s.n) { sx[k] = x; sy[k] = y; sy[s.n + (k)] = z; }   // winner look-up table (x | y | z), 12*n bytes
         }
         pz[i] = z;
         tmp[i] = 1e10f;
@@ -87,7 +88,8 @@ __device__ __forceinline__ void fps_segment(const FpsSeg& s, int T_ref, float* s
     int old = 0;
     for (int j = 1; j < s.m; ++j) {
         float x1, y1, z1;
-        fps_load<PACKED>(s, old, x1, y1, z1);
+        if constexpr (SMEM_XY) fps_load<PACKED>(s, old, x1, y1, z1);        // large clouds: z is not staged, read it back from L1/L2
+        else { x1 = sx[old]; y1 = sy[old]; z1 = sy[s.n + old]; }             // broadcast shared-memory reads (~30 cycles)
         unsigned bv = 0u, bt = 0u;
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
@@ -300,7 +302,7 @@ ETCH_API int etch_fps_bcn(const float* xyz, int B, int n, int m, int* idx, cudaS
 #define L(P, SX)                                                                                               \
     {                                                                                                          \
         auto kern = fps_bcn_kernel<P, SX>;                                                                     \
-        const size_t sm = (SX) ? (size_t)n * 8 : 0;                                                            \
+        const size_t sm = (SX) ? (size_t)n * 8 : (size_t)n * 12;                                               \
         if (sm > 48 * 1024) ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         kern<<<B, nt, sm, stream>>>(xyz, n, m, T, idx);                                                        \
     }
@@ -324,7 +326,7 @@ ETCH_API int etch_fps_packed(int b, int n_max, const float* xyz, const int* offs
 #define L(P, SX)                                                                                               \
     {                                                                                                          \
         auto kern = fps_packed_kernel<P, SX>;                                                                  \
-        const size_t sm = (SX) ? (size_t)n_max * 8 : 0;                                                        \
+        const size_t sm = (SX) ? (size_t)n_max * 8 : (size_t)n_max * 12;                                       \
         if (sm > 48 * 1024) ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         kern<<<b, nt, sm, stream>>>(xyz, offset, new_offset, T, idx);                                          \
     }

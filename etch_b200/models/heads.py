@@ -156,7 +156,8 @@ class PTPlan:
             k = sd[prefix + "cls.3.weight"].shape[0]
             w0 = sd[prefix + "confi.0.weight"].squeeze(-1).float().cpu()  # [K*128, 128]
             hi, lo = tc.split_tf32(w0)
-            tile = lambda t: t.view(k * 4, 32, 32, 4).permute(0, 2, 1, 3)  # noqa: E731  [chunk][k/4][n][4]
+            # [group l][row u (128)][K quarter kq (4)][k/4 (8)][4] -> [l][kq][k/4][u][4]: one [128 x 32] slice per (group, quarter)
+            tile = lambda t: t.view(k, 128, 4, 8, 4).permute(0, 2, 3, 1, 4).reshape(k * 4, 8, 128, 4)  # noqa: E731
             W0c = torch.stack([tile(hi), tile(lo)], 1).contiguous().to(device)
             self.head = dict(kind="conf", K=k, W0c=W0c, Wc0t=_wt(sd[prefix + "cls.0.weight"].squeeze(-1), d), sc=s, hc=h,
                              Wc3t=_wt(sd[prefix + "cls.3.weight"].squeeze(-1), d), bc3=sd[prefix + "cls.3.bias"].to(**d).contiguous(),

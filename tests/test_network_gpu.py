@@ -169,4 +169,4 @@ def test_scan_fitter_graph_replay_matches_eager(cuda):
         out2 = graphed(pts.pin_memory(), device=cuda)
         torch.cuda.synchronize()
         assert (out2["vertices"] - ref["vertices"]).norm(dim=-1).mean().item() * 1000.0 < 0.05
-    assert graphed.launches_per_step > 500
+    assert graphed.launches_per_step > 100
