@@ -40,3 +40,10 @@ static inline int etch_opt_n_threads(int work_size) {
     if (t < 1) t = 1;
     return t;
 }
+
+// 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
+__device__ __forceinline__ void etch_ldg256(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}

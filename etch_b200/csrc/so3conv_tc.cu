@@ -33,8 +33,24 @@ __device__ __forceinline__ void stats_to_affine_tc(const double* sums, int b, in
 
 using umma::bulk_load;
 
+__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Warp-specialised pipeline: warps 0-7 (256 threads) stage the activations, gather + split one A tile per anchor-neighbour
+// slot j into a 2-deep ring, and run the epilogue; warp 8 streams the weight slices (cp.async.bulk ring) and issues the
+// tcgen05.mma's, so the fill of slot j+1 overlaps the MMAs of slot j and nobody waits for an MMA to retire except
+// through the ring's mbarriers.
+template <int CIN, int COUT, int J>
+struct AgemmCfg {
+    static constexpr int LD = CIN + 4;
+    static constexpr uint32_t A_BYTES = MROWS * CIN * 4;     // one (hi or lo) A tile
+    static constexpr uint32_t B_BYTES = COUT * CIN * 4;      // one (hi or lo) weight slice
+    static constexpr int WR = (2 * B_BYTES <= 16384) ? 4 : 2; // weight ring depth
+    static constexpr size_t smem = (size_t)4 * A_BYTES + (size_t)WR * 2 * B_BYTES + (size_t)NPAIR * LD * 4 + (size_t)2 * CIN * 4 +
+                                   (size_t)((NA * J + 15) / 16) * 16 + 128;
+};
+
 template <int CIN, int COUT, int J, bool NORM_IN>
-__global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
+__global__ void __launch_bounds__(288, 1) anchor_gemm_tc_kernel(
     const float* __restrict__ xin,       // [B,Q,60,CIN]
     const int* __restrict__ src_idx,     // [B,P] or nullptr
     const int* __restrict__ tab,         // [60][J]
@@ -43,135 +59,150 @@ __global__ void __launch_bounds__(256, 1) anchor_gemm_tc_kernel(
     const double* __restrict__ in_stats, double in_count, int Q, int P,
     float* __restrict__ zraw, double* __restrict__ stats)
 {
-    constexpr int LD = CIN + 4;
-    constexpr uint32_t A_BYTES = MROWS * CIN * 4;     // one (hi or lo) A tile
-    constexpr uint32_t B_BYTES = COUT * CIN * 4;      // one (hi or lo) weight slice
+    using Cfg = AgemmCfg<CIN, COUT, J>;
+    constexpr int LD = Cfg::LD;
+    constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
+    constexpr int WR = Cfg::WR;
     constexpr int TCOLS = COUT < 32 ? 32 : COUT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* s_A = smem_raw;                                   // [hi | lo]
-    unsigned char* s_B = s_A + 2 * A_BYTES;                          // [2 buffers][hi | lo]
-    float* s_x = reinterpret_cast<float*>(s_B + 4 * B_BYTES);        // [120][LD]
+    unsigned char* s_A = smem_raw;                                   // [2 buffers][hi | lo]
+    unsigned char* s_B = s_A + 4 * A_BYTES;                          // [WR buffers][hi | lo]
+    float* s_x = reinterpret_cast<float*>(s_B + WR * 2 * B_BYTES);   // [120][LD]
     float* s_mean = s_x + NPAIR * LD;
     float* s_rstd = s_mean + CIN;
-    int* s_tab = reinterpret_cast<int*>(s_rstd + CIN);               // [60][J]
+    unsigned char* s_tab = reinterpret_cast<unsigned char*>(s_rstd + CIN);   // [60][J]
     float* s_z = reinterpret_cast<float*>(s_A);                      // epilogue reuse [128][COUT]
-    __shared__ uint64_t bar_mma, bar_b[2];
+    __shared__ uint64_t a_full[2], a_free[2], w_full[WR], w_free[WR], acc_full;
     __shared__ uint32_t tmem_base;
 
-    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < NA * J; i += 256) s_tab[i] = __ldg(tab + i);
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < NA * J; i += 288) s_tab[i] = (unsigned char)__ldg(tab + i);
     if (NORM_IN) stats_to_affine_tc(in_stats, b, CIN, in_count, s_mean, s_rstd);
-    if (warp == 0) umma::tmem_alloc(&tmem_base, TCOLS);
-    if (tid == 0) { umma::mbar_init(&bar_mma, 1); umma::mbar_init(&bar_b[0], 1); umma::mbar_init(&bar_b[1], 1); }
+    if (warp == 8) umma::tmem_alloc(&tmem_base, TCOLS);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&a_full[i], 8); umma::mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < WR; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_free[i], 1); }
+        umma::mbar_init(&acc_full, 1);
+    }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = umma::uniform(tmem_base);
-    uint32_t n_mma = 0, n_b[2] = {0, 0};   // completed phases per barrier (uniform across threads)
-    double acc_s = 0.0, acc_ss = 0.0;
     const int ntiles = (P + TP - 1) / TP;
-    // fill mapping: 2 threads per GEMM row, each half of the channels
-    const int frow = tid >> 1, fhalf = tid & 1;
-    const int fpair = frow < NPAIR ? frow : -1;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int p0 = tile * TP;
-        const int npts = min(TP, P - p0);
-        // first weight slice of this tile (buffer 0 is free: every MMA of the previous tile has completed)
-        if (warp == 0) bulk_load(s_B, Wc, 2 * B_BYTES, &bar_b[0]);
-        // stage (and normalise) the activations of the tile's points; zero the pad rows of the A tiles
-        for (int t = tid; t < NPAIR * (CIN / 4); t += 256) {
-            const int row = t / (CIN / 4), c4 = t % (CIN / 4);
-            const int pl = row / NA;
-            const int p = min(p0 + pl, P - 1);
-            const int sp = src_idx ? __ldg(src_idx + (size_t)b * P + p) : p;
-            float4 v = __ldg(reinterpret_cast<const float4*>(xin + (((size_t)b * Q + sp) * NA + (row % NA)) * CIN) + c4);
-            if (NORM_IN) {
-                const int c = c4 * 4;
-                v.x = etch_lrelu((v.x - s_mean[c]) * s_rstd[c]);
-                v.y = etch_lrelu((v.y - s_mean[c + 1]) * s_rstd[c + 1]);
-                v.z = etch_lrelu((v.z - s_mean[c + 2]) * s_rstd[c + 2]);
-                v.w = etch_lrelu((v.w - s_mean[c + 3]) * s_rstd[c + 3]);
+    if (warp == 8) {
+        // ===== weight streaming + MMA issue (warp-collective) =====
+        const uint32_t total = (uint32_t)my_tiles * J;
+        uint32_t issued = 0;
+        for (uint32_t g = 0; g < total; ++g) {
+            while (issued < total && issued < g + WR) {
+                const uint32_t wb = issued % WR, use = issued / WR;
+                if (use > 0) umma::mbar_wait(&w_free[wb], (use - 1) & 1);
+                bulk_load(s_B + wb * 2 * B_BYTES, Wc + (size_t)(issued % J) * 2 * COUT * CIN, 2 * B_BYTES, &w_full[wb]);
+                ++issued;
             }
-            *reinterpret_cast<float4*>(s_x + row * LD + c4 * 4) = v;
-        }
-        for (int t = tid; t < (MROWS - NPAIR) * (CIN / 4) * 2; t += 256) {  // rows 120..127 of hi and lo stay zero
-            const int which = t / ((MROWS - NPAIR) * (CIN / 4)), rem = t % ((MROWS - NPAIR) * (CIN / 4));
-            const int r = NPAIR + rem / (CIN / 4), kc = rem % (CIN / 4);
-            *reinterpret_cast<float4*>(s_A + which * A_BYTES + kc * (MROWS * 16) + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-
-        for (int j = 0; j < J; ++j) {
-            // gather + split the A tile for slot j
-            if (fpair >= 0) {
-                const int pl = fpair / NA, a = fpair % NA;
-                const float* xr = s_x + (pl * NA + s_tab[a * J + j]) * LD + fhalf * (CIN / 2);
-#pragma unroll
-                for (int c4 = 0; c4 < CIN / 8; ++c4) {
-                    const float4 v = *reinterpret_cast<const float4*>(xr + c4 * 4);
-                    float4 h, l;
-                    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
-                    umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
-                    const int kc = fhalf * (CIN / 8) + c4;
-                    *reinterpret_cast<float4*>(s_A + kc * (MROWS * 16) + frow * 16) = h;
-                    *reinterpret_cast<float4*>(s_A + A_BYTES + kc * (MROWS * 16) + frow * 16) = l;
-                }
-            }
-            umma::fence_async_smem();
-            __syncthreads();
-            if (warp == 0) {
-                const int buf = j & 1;
-                if (j + 1 < J) {  // prefetch the next slice into the other buffer (its last reader, MMA j-1, has completed)
-                    bulk_load(s_B + (buf ^ 1) * 2 * B_BYTES, Wc + (size_t)(j + 1) * 2 * COUT * CIN, 2 * B_BYTES, &bar_b[buf ^ 1]);
-                }
-                umma::mbar_wait(&bar_b[buf], n_b[buf] & 1);
-                umma::fence_after_sync();
-                const uint32_t a_hi = umma::smem_u32(s_A), a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
-                umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, CIN, COUT, j > 0);
-                umma::commit(&bar_mma);
-            }
-            n_b[j & 1]++;
-            // the A tile may only be overwritten once the MMAs reading it are done
-            umma::mbar_wait(&bar_mma, n_mma & 1);
-            n_mma++;
+            const uint32_t wb = g % WR, ab = g & 1, j = g % J;
+            umma::mbar_wait(&w_full[wb], (g / WR) & 1);
+            umma::mbar_wait(&a_full[ab], (g >> 1) & 1);
             umma::fence_after_sync();
+            const uint32_t a_hi = umma::smem_u32(s_A + ab * 2 * A_BYTES), a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = umma::smem_u32(s_B + wb * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
+            umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, CIN, COUT, j > 0);
+            umma::commit(&a_free[ab]);
+            umma::commit(&w_free[wb]);
+            if (j == J - 1) umma::commit(&acc_full);
         }
-        // ---- epilogue: TMEM -> registers -> (+bias) -> shared tile ----
-        {
-            const int q = warp & 3, half = warp >> 2;
-            const int row = q * 32 + (tid & 31);
-#pragma unroll
-            for (int c0 = 0; c0 < COUT / 2; c0 += 8) {
-                float v[8];
-                const int col = half * (COUT / 2) + c0;
-                umma::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + col, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s_z[row * COUT + col + i] = v[i] + __ldg(bias + col + i);
+    } else {
+        // ===== activation staging, A-tile fills, epilogue =====
+        constexpr int RG = 256 / COUT;                     // row groups of the statistics pass
+        const int scol = tid % COUT, srg = tid / COUT;
+        double acc_s = 0.0, acc_ss = 0.0;
+        const int frow = tid & 127, fhalf = tid >> 7;      // fill mapping: row, channel half
+        const bool fok = frow < NPAIR;
+        const int fpl = fok ? frow / NA : 0, fa = fok ? frow % NA : 0;
+        uint32_t g = 0, ntile_done = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int p0 = tile * TP;
+            const int npts = min(TP, P - p0);
+            // stage (and normalise) the activations of the tile's points
+            for (int t = tid; t < NPAIR * (CIN / 4); t += 256) {
+                const int row = t / (CIN / 4), c4 = t % (CIN / 4);
+                const int pl = row / NA;
+                const int p = min(p0 + pl, P - 1);
+                const int sp = src_idx ? __ldg(src_idx + (size_t)b * P + p) : p;
+                float4 v = __ldg(reinterpret_cast<const float4*>(xin + (((size_t)b * Q + sp) * NA + (row % NA)) * CIN) + c4);
+                if (NORM_IN) {
+                    const int c = c4 * 4;
+                    v.x = etch_lrelu((v.x - s_mean[c]) * s_rstd[c]);
+                    v.y = etch_lrelu((v.y - s_mean[c + 1]) * s_rstd[c + 1]);
+                    v.z = etch_lrelu((v.z - s_mean[c + 2]) * s_rstd[c + 2]);
+                    v.w = etch_lrelu((v.w - s_mean[c + 3]) * s_rstd[c + 3]);
+                }
+                *reinterpret_cast<float4*>(s_x + row * LD + c4 * 4) = v;
             }
+            compute_warps_sync();
+
+            for (int j = 0; j < J; ++j, ++g) {
+                const uint32_t ab = g & 1;
+                if (g >= 2) umma::mbar_wait(&a_free[ab], ((g >> 1) - 1) & 1);
+                if (fok) {   // rows 120..127 are never written: their (garbage) products land in TMEM rows that are never read
+                    const float* xr = s_x + (fpl * NA + s_tab[fa * J + j]) * LD + fhalf * (CIN / 2);
+                    unsigned char* dh = s_A + ab * 2 * A_BYTES + frow * 16;
+#pragma unroll
+                    for (int c4 = 0; c4 < CIN / 8; ++c4) {
+                        const float4 v = *reinterpret_cast<const float4*>(xr + c4 * 4);
+                        float4 h, l;
+                        umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+                        umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+                        const int kc = fhalf * (CIN / 8) + c4;
+                        *reinterpret_cast<float4*>(dh + kc * (MROWS * 16)) = h;
+                        *reinterpret_cast<float4*>(dh + A_BYTES + kc * (MROWS * 16)) = l;
+                    }
+                }
+                umma::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&a_full[ab]);
+            }
+            // ---- epilogue: TMEM -> registers -> (+bias) -> shared tile (aliases the A ring: every MMA has retired) ----
+            umma::mbar_wait(&acc_full, ntile_done & 1);
+            ++ntile_done;
+            umma::fence_after_sync();
+            {
+                const int q = warp & 3, half = warp >> 2;
+                const int row = q * 32 + lane;
+#pragma unroll
+                for (int c0 = 0; c0 < COUT / 2; c0 += 8) {
+                    float v[8];
+                    const int col = half * (COUT / 2) + c0;
+                    umma::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + col, v);
+                    float4 o0, o1;
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                    o0 = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
+                    o1 = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
+                    *reinterpret_cast<float4*>(s_z + row * COUT + col) = o0;
+                    *reinterpret_cast<float4*>(s_z + row * COUT + col + 4) = o1;
+                }
+            }
+            umma::fence_before_sync();
+            compute_warps_sync();
+            const int nvalid = npts * NA;
+            float* dst = zraw + ((size_t)b * P + p0) * NA * COUT;
+            for (int i = tid; i < nvalid * COUT / 4; i += 256)
+                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_z)[i];
+            {
+                float s = 0.f, ss = 0.f;
+                for (int r = srg; r < nvalid; r += RG) { const float v = s_z[r * COUT + scol]; s += v; ss = fmaf(v, v, ss); }
+                acc_s += (double)s; acc_ss += (double)ss;
+            }
+            compute_warps_sync();   // s_z (= A ring) and s_x are free for the next tile
         }
-        umma::fence_before_sync();
-        __syncthreads();
-        umma::fence_after_sync();
-        const int nvalid = npts * NA;
-        float* dst = zraw + ((size_t)b * P + p0) * NA * COUT;
-        for (int i = tid; i < nvalid * COUT / 4; i += 256)
-            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_z)[i];
-        if (tid < COUT) {
-            float s = 0.f, ss = 0.f;
-            for (int r = 0; r < nvalid; ++r) { const float v = s_z[r * COUT + tid]; s += v; ss = fmaf(v, v, ss); }
-            acc_s += (double)s; acc_ss += (double)ss;
-        }
-        __syncthreads();  // s_z aliases the A tiles
-    }
-    if (tid < COUT) {
-        atomicAdd(stats + ((size_t)b * COUT + tid) * 2, acc_s);
-        atomicAdd(stats + ((size_t)b * COUT + tid) * 2 + 1, acc_ss);
+        atomicAdd(stats + ((size_t)b * COUT + scol) * 2, acc_s);
+        atomicAdd(stats + ((size_t)b * COUT + scol) * 2 + 1, acc_ss);
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, TCOLS);
+    if (warp == 8) umma::tmem_dealloc(tmem, TCOLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -265,21 +296,29 @@ __global__ void __launch_bounds__(256, 1) inter_conv_tc_kernel(
 #pragma unroll
                 for (int i = 0; i < 6; ++i) kq[i] = s_krs[a * NK + kg * 6 + i];
                 const float* fa = F + a * CIN + c0;
-                float4 f0 = __ldg(reinterpret_cast<const float4*>(fa + s_off[pl * NN]));
-                float4 f1 = __ldg(reinterpret_cast<const float4*>(fa + s_off[pl * NN]) + 1);
-#pragma unroll 2
-                for (int n = 0; n < NN; ++n) {
-                    const float4 g = s_g[pl * NN + n];
-                    const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-                    if (n + 1 < NN) {
-                        const float4* fp = reinterpret_cast<const float4*>(fa + s_off[pl * NN + n + 1]);
-                        f0 = __ldg(fp); f1 = __ldg(fp + 1);
-                    }
+                // The kernel is bound by L1 wavefronts (one per distinct 128-B line per load instruction): fetch the 8 channels of a
+                // neighbour with ONE 256-bit load, and keep PF neighbours in flight per thread.
+                constexpr int PF = 4;
+                static_assert(NN % PF == 0, "neighbour count must be a multiple of the prefetch depth");
+                float fb[PF][8];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        const float w = fmaxf(fmaf(g.x, kq[i].x, fmaf(g.y, kq[i].y, fmaf(g.z, kq[i].z, g.w - kq[i].w))), 0.f);
+                for (int j = 0; j < PF; ++j) etch_ldg256(fa + s_off[pl * NN + j], fb[j]);
+#pragma unroll 1
+                for (int n0 = 0; n0 < NN; n0 += PF) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[c][i] = fmaf(fv[c], w, acc[c][i]);
+                    for (int j = 0; j < PF; ++j) {
+                        const int n = n0 + j;
+                        const float4 g = s_g[pl * NN + n];
+                        float fv[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) fv[c] = fb[j][c];
+                        if (n + PF < NN) etch_ldg256(fa + s_off[pl * NN + n + PF], fb[j]);
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            const float w = fmaxf(fmaf(g.x, kq[i].x, fmaf(g.y, kq[i].y, fmaf(g.z, kq[i].z, g.w - kq[i].w))), 0.f);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) acc[c][i] = fmaf(fv[c], w, acc[c][i]);
+                        }
                     }
                 }
             }
@@ -362,13 +401,14 @@ int grid_for_tc(int ntiles, int B) {
 template <int CIN, int COUT, int J, bool NORM>
 int launch_agemm_tc(const float* xin, const int* src_idx, const int* tab, const float* Wc, const float* bias,
                     const double* in_stats, double in_count, int B, int Q, int P, float* zraw, double* stats, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)2 * MROWS * CIN * 4 + (size_t)4 * COUT * CIN * 4 + (size_t)NPAIR * (CIN + 4) * 4 +
-                            (size_t)2 * CIN * 4 + (size_t)NA * J * 4 + 128;
-    static_assert((size_t)MROWS * COUT * 4 <= (size_t)2 * MROWS * CIN * 4, "epilogue tile must fit the A region");
+    using Cfg = AgemmCfg<CIN, COUT, J>;
+    static_assert((size_t)MROWS * COUT * 4 <= (size_t)4 * Cfg::A_BYTES, "epilogue tile must fit the A ring");
+    static_assert(Cfg::smem <= 227 * 1024, "shared memory budget");
+    static_assert(256 % COUT == 0, "statistics pass mapping");
     auto kern = anchor_gemm_tc_kernel<CIN, COUT, J, NORM>;
-    ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
     dim3 grid(grid_for_tc((P + TP - 1) / TP, B), B);
-    kern<<<grid, 256, smem, stream>>>(xin, src_idx, tab, Wc, bias, in_stats, in_count, Q, P, zraw, stats);
+    kern<<<grid, 288, Cfg::smem, stream>>>(xin, src_idx, tab, Wc, bias, in_stats, in_count, Q, P, zraw, stats);
     ETCH_RETURN_LAST();
 }
 
