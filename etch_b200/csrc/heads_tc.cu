@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     const float* __restrict__ bf,      // [128]
     const float* __restrict__ vreg,    // [128]
     float creg, const float* __restrict__ anchors, int N, int S,
-    float* __restrict__ dir, float* __restrict__ anc_w)
+    double* __restrict__ ce_out, float* __restrict__ anc_w)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* s_X = smem_raw;                         // [hi|lo] tokens
@@ -488,22 +488,31 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             if (anc_w && tid < 2 * DH_NA && p0 + tid / DH_NA < N) anc_w[((size_t)b * N + p0) * DH_NA + tid] = w;
         }
         __syncthreads();
-        if (tid < 2 && p0 + tid < N) {
-            double Ce[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-            for (int a = 0; a < DH_NA; ++a) {
-                const float wa = s_w[tid * DH_NA + a];
-                for (int e = 0; e < 9; ++e) Ce[e / 3][e % 3] += (double)(wa * s_anc[a * 9 + e]);
-            }
-            float d[3];
-            dh_so3_direction(Ce, d);
-            float* o = dir + ((size_t)b * N + p0 + tid) * 3;
-            o[0] = d[0]; o[1] = d[1]; o[2] = d[2];
+        // chordal-mean matrix Ce = sum_a w_a R_a of the tile's two points (18 entries, one thread each); the 3x3 SVD that
+        // turns it into a direction runs in so3_direction_kernel, off this kernel's critical path
+        if (tid < 18 && p0 + tid / 9 < N) {
+            const int pl = tid / 9, e = tid % 9;
+            double acc = 0.0;
+            for (int a = 0; a < DH_NA; ++a) acc += (double)(s_w[pl * DH_NA + a] * s_anc[a * 9 + e]);
+            ce_out[((size_t)b * N + p0 + pl) * 9 + e] = acc;
         }
         // the next tile's blend overwrites X only; s_w / s_part are rewritten after further barriers
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// direction[pt] = third column of the rotation closest to Ce[pt] (src/models/models_pointcloud.py so3_mean): one thread per point
+__global__ void __launch_bounds__(128) so3_direction_kernel(const double* __restrict__ ce, int total_pts, float* __restrict__ dir) {
+    const int pt = blockIdx.x * 128 + threadIdx.x;
+    if (pt >= total_pts) return;
+    double Ce[3][3];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Ce[e / 3][e % 3] = ce[(size_t)pt * 9 + e];
+    float d[3];
+    dh_so3_direction(Ce, d);
+    dir[(size_t)pt * 3] = d[0]; dir[(size_t)pt * 3 + 1] = d[1]; dir[(size_t)pt * 3 + 2] = d[2];
 }
 
 // inv[b,n,:] = sum_k w_k * mean_a feats[b, idx_k, a, :]   (anchor mean commutes with the 3-NN blend)
@@ -533,12 +542,14 @@ __global__ void __launch_bounds__(256) interp_inv_kernel(const float* __restrict
 }  // namespace
 
 // Tensor-core decode_direction. wall = the 18 weight slices [18][2][8][64][4] (see etch_b200/models/heads.py::DirectionPlan).
-// fmean_scratch [B,S,64] is caller-owned scratch for the per-coarse-point anchor mean.
+// scratch: caller-owned, B*S*64 + B*N*18 floats (per-coarse-point anchor mean, then the [B,N,9] double chordal-mean matrices).
 ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const float* up_w, const float* wall,
                                     const float* bc1, const float* bf, const float* vreg, float creg, const float* anchors,
-                                    int B, int N, int S, float* dir, float* inv, float* anc_w, float* fmean_scratch,
+                                    int B, int N, int S, float* dir, float* inv, float* anc_w, float* scratch,
                                     cudaStream_t stream) {
-    if (!feats || !up_idx || !up_w || !wall || !bc1 || !bf || !vreg || !anchors || !dir || !inv || !fmean_scratch) return ETCH_EINVAL;
+    if (!feats || !up_idx || !up_w || !wall || !bc1 || !bf || !vreg || !anchors || !dir || !inv || !scratch) return ETCH_EINVAL;
+    float* fmean_scratch = scratch;
+    double* ce = reinterpret_cast<double*>(scratch + (size_t)B * S * 64);
     anchor_mean_kernel<<<etch_cdiv(B * S, 4), 256, 0, stream>>>(feats, B * S, fmean_scratch);
     dim3 g2(etch_cdiv(N, 4), B);
     interp_inv_kernel<<<g2, 256, 0, stream>>>(fmean_scratch, up_idx, up_w, N, S, inv);
@@ -549,6 +560,7 @@ ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
     dim3 grid(gx, B);
-    direction_head_tc_kernel<<<grid, 256, smem, stream>>>(feats, up_idx, up_w, wall, bc1, bf, vreg, creg, anchors, N, S, dir, anc_w);
+    direction_head_tc_kernel<<<grid, 256, smem, stream>>>(feats, up_idx, up_w, wall, bc1, bf, vreg, creg, anchors, N, S, ce, anc_w);
+    so3_direction_kernel<<<etch_cdiv(B * N, 128), 128, 0, stream>>>(ce, B * N, dir);
     ETCH_RETURN_LAST();
 }

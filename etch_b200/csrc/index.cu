@@ -289,6 +289,113 @@ __global__ void __launch_bounds__(64) knn_packed_kernel(int m, int nsample_rt, c
     }
 }
 
+// ---- warp-per-query kNN (nsample <= 32) ----
+// The reference keeps a max-heap of the nsample best and replaces its root whenever a candidate is strictly closer
+// (knnquery_cuda_kernel.cu:50-75): the kept set is "the nsample smallest by (distance, scan order)" and, when no two kept
+// distances are equal, the heap-sorted output is simply ascending distance.  A warp therefore keeps the list SORTED, one
+// entry per lane: 32 candidates are evaluated per step, the few that beat the current nsample-th distance are inserted in
+// index order with a ballot + shuffle shift.  If an insertion ever meets an equal distance already in the list (the only
+// situation in which heap layout decides the result), the query is recomputed by knn_serial_exact, the literal emulation.
+template <int NS>
+__device__ __noinline__ void knn_serial_exact(int start, int end, float qx, float qy, float qz, const float* __restrict__ xyz,
+                                              int* __restrict__ out_idx, float* __restrict__ out_d) {
+    float best_dist[NS];
+    int best_idx[NS];
+    for (int i = 0; i < NS; ++i) { best_dist[i] = 1e10f; best_idx[i] = start; }
+    for (int i = start; i < end; ++i) {
+        const float d2 = etch_sqdist3(qx - __ldg(xyz + (size_t)i * 3), qy - __ldg(xyz + (size_t)i * 3 + 1), qz - __ldg(xyz + (size_t)i * 3 + 2));
+        if (d2 < best_dist[0]) {
+            best_dist[0] = d2;
+            best_idx[0] = i;
+            knn_reheap<NS>(best_dist, best_idx, NS);
+        }
+    }
+    for (int i = NS - 1; i > 0; i--) {
+        const float tf = best_dist[0]; best_dist[0] = best_dist[i]; best_dist[i] = tf;
+        const int ti = best_idx[0]; best_idx[0] = best_idx[i]; best_idx[i] = ti;
+        knn_reheap<NS>(best_dist, best_idx, i);
+    }
+    for (int i = 0; i < NS; ++i) { out_idx[i] = best_idx[i]; out_d[i] = best_dist[i]; }
+}
+
+constexpr int KNNW_TILE = 1024;   // candidates staged per step (SoA, 12 KB)
+constexpr int KNNW_WARPS = 8;
+
+template <int NS>
+__global__ void __launch_bounds__(KNNW_WARPS * 32) knn_warp_kernel(int m, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                                                   const int* __restrict__ offset, const int* __restrict__ new_offset,
+                                                                   int nbatch, int* __restrict__ idx, float* __restrict__ dist2) {
+    static_assert(NS >= 1 && NS <= 32, "one list entry per lane");
+    __shared__ float tx[KNNW_TILE], ty[KNNW_TILE], tz[KNNW_TILE];
+    __shared__ int s_lo, s_hi;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * KNNW_WARPS + warp;
+    const bool active = pt < m;
+    int start = 0, end = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        int bt = 0;
+        while (bt < nbatch - 1 && !(pt < __ldg(new_offset + bt))) bt++;
+        start = bt == 0 ? 0 : __ldg(offset + bt - 1);
+        end = __ldg(offset + bt);
+        qx = __ldg(new_xyz + (size_t)pt * 3); qy = __ldg(new_xyz + (size_t)pt * 3 + 1); qz = __ldg(new_xyz + (size_t)pt * 3 + 2);
+    }
+    if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = 0; }
+    __syncthreads();
+    if (active && lane == 0) { atomicMin(&s_lo, start); atomicMax(&s_hi, end); }
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi;
+
+    float ld = 1e10f;       // lane l < NS: l-th smallest distance so far
+    int li = start;
+    float tau = 1e10f;      // NS-th smallest (warp-uniform)
+    bool tie = false;
+
+    for (int t0 = lo; t0 < hi; t0 += KNNW_TILE) {
+        const int cntp = min(KNNW_TILE, hi - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cntp * 3; i += KNNW_WARPS * 32) {
+            const float v = __ldg(xyz + (size_t)t0 * 3 + i);
+            const int c = i / 3, k = i - c * 3;
+            (k == 0 ? tx : (k == 1 ? ty : tz))[c] = v;
+        }
+        __syncthreads();
+        if (!active) continue;
+        const int a = max(start, t0) - t0, e = min(end, t0 + cntp) - t0;
+        for (int c0 = a; c0 < e; c0 += 32) {
+            const int c = c0 + lane;
+            float d = 3e38f;
+            if (c < e) d = etch_sqdist3(qx - tx[c], qy - ty[c], qz - tz[c]);
+            unsigned mask = __ballot_sync(0xffffffffu, d < tau);
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float dc = __shfl_sync(0xffffffffu, d, l);
+                if (dc < tau) {   // against the CURRENT nsample-th distance, as the serial scan would see it
+                    const unsigned le = __ballot_sync(0xffffffffu, lane < NS && ld <= dc);
+                    const int pos = __popc(le);
+                    const unsigned eq = __ballot_sync(0xffffffffu, lane < NS && ld == dc);
+                    tie |= eq != 0u;
+                    const float pd = __shfl_up_sync(0xffffffffu, ld, 1);
+                    const int pi = __shfl_up_sync(0xffffffffu, li, 1);
+                    if (lane > pos) { ld = pd; li = pi; }
+                    if (lane == pos) { ld = dc; li = t0 + c0 + l; }
+                    tau = __shfl_sync(0xffffffffu, ld, NS - 1);
+                }
+            }
+        }
+    }
+    if (!active) return;
+    if (tie) {
+        if (lane == 0) knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, idx + (size_t)pt * NS, dist2 + (size_t)pt * NS);
+        return;
+    }
+    if (lane < NS) {
+        idx[(size_t)pt * NS + lane] = li;
+        dist2[(size_t)pt * NS + lane] = ld;
+    }
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -362,10 +469,10 @@ ETCH_API int etch_knn_packed(int m, int nsample, const float* xyz, const float* 
                              const int* new_offset, int nbatch, int* idx, float* dist2, cudaStream_t stream) {
     if (!xyz || !new_xyz || !offset || !new_offset || !idx || !dist2 || m <= 0 || nsample <= 0 || nsample > 100 || nbatch <= 0)
         return ETCH_EINVAL;
-    const int grid = etch_cdiv(m, 64);
-    if (nsample == 3) knn_packed_kernel<3><<<grid, 64, 0, stream>>>(m, 3, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
-    else if (nsample == 8) knn_packed_kernel<8><<<grid, 64, 0, stream>>>(m, 8, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
-    else if (nsample == 16) knn_packed_kernel<16><<<grid, 64, 0, stream>>>(m, 16, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    const int grid = etch_cdiv(m, 64), wgrid = etch_cdiv(m, KNNW_WARPS);
+    if (nsample == 3) knn_warp_kernel<3><<<wgrid, KNNW_WARPS * 32, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else if (nsample == 8) knn_warp_kernel<8><<<wgrid, KNNW_WARPS * 32, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    else if (nsample == 16) knn_warp_kernel<16><<<wgrid, KNNW_WARPS * 32, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
     else knn_packed_kernel<0><<<grid, 64, 0, stream>>>(m, nsample, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
     ETCH_RETURN_LAST();
 }

@@ -69,7 +69,7 @@ def run_direction(plan, hitpts, xyz2_b3s, feats2, want_anchor_weights=False):
     inv = torch.empty(B, N, 64, dtype=torch.float32, device=dev)
     anc_w = torch.empty(B, N, 60, dtype=torch.float32, device=dev) if want_anchor_weights else None
     if USE_TC:
-        fmean = torch.empty(B, S, 64, dtype=torch.float32, device=dev)
+        fmean = torch.empty(B * S * 64 + B * N * 18, dtype=torch.float32, device=dev)   # anchor means + [B,N,9] double Ce
         L.call("direction_head_tc", L.ptr(feats2), L.ptr(up_idx), L.ptr(up_w), L.ptr(plan.wall), L.ptr(plan.bc1), L.ptr(plan.bf),
                L.ptr(plan.vreg), L.f32(plan.creg), L.ptr(plan.anchors), B, N, S, L.ptr(direction), L.ptr(inv), L.ptr(anc_w), L.ptr(fmean))
     else:
