@@ -142,6 +142,55 @@ int etch_lbs_forward(const float* params, const float* v_template, const float* 
                      const float* weights, const float* Jt, const float* Js, const int* parents, const int* extra_vids, int B,
                      int V, float* verts, float* joints, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM variants of the GEMM-shaped stages (the product path; the CUDA-core entry points above remain as the
+ * ETCH_B200_NO_TC=1 reference build of the same operators).  All GEMMs run as 3xTF32 (hi*hi + lo*hi + hi*lo, fp32
+ * accumulate in TMEM), so results stay at fp32-level accuracy against the reference's fp32 cuBLAS/einsum path.  Weight
+ * operands arrive pre-split into (hi, lo) TF32 pairs and pre-tiled in the canonical K-major UMMA layout
+ * (element (r, k) of an [R x K] tile at byte (k/4)*(R*16) + r*16 + (k%4)*4); etch_b200/models/tc.py builds them once per
+ * checkpoint. */
+
+/* InterSO3Conv (vgtk/so3conv/functional.py:286-324, modules.py:19-39): neighbour contraction on the CUDA cores, channel
+ * mixing on tcgen05.  Wc [cin/8*2][2][24][cout][4]: slabs of 96 K-columns, K'' = kgl*48 + c*6 + i. (cin,cout,nn) in
+ * {(32,32,32),(32,64,64),(64,64,32)}. */
+int etch_so3_inter_conv_tc(const float* xyz, const float* feat, const int* sample_idx, const int* nbr, const float* krs,
+                           const float* Wc, const float* bias, int B, int q, int P, int nn, int cin, int cout, float sigma,
+                           float* zraw, double* stats, cudaStream_t stream);
+
+/* IntraSO3Conv (functional.py:331-343, modules.py:131-153). Wc [12][2][c/4][cout][4]. */
+int etch_so3_intra_conv_tc(const float* zin, const double* in_stats, const int* intra_idx, const float* Wc, const float* bias,
+                           int B, int P, int c, int cout, float* zraw, double* stats, cudaStream_t stream);
+
+/* skip 1x1 conv of a residual block (src/models/so3conv.py:178-180). Wc [1][2][cin/4][cout][4]. */
+int etch_so3_skip_conv_tc(const float* feat, const int* sample_idx, const int* ident, const float* Wc, const float* bias,
+                          int B, int q, int P, int cin, int cout, float* zraw, double* stats, cudaStream_t stream);
+
+/* decode_direction (src/models/models_pointcloud.py:102-131; src/models/so3conv.py:186-225): 3-NN blend, 2 x MHSA over the 60
+ * anchor tokens, fused MLP + so3_reg, chordal SO(3) mean.  wall [18][2][8][64][4] (etch_b200/models/heads.py::DirectionPlan);
+ * scratch: B*S*64 + B*N*18 floats, caller-owned. */
+int etch_direction_head_tc(const float* feats, const int* up_idx, const float* up_w, const float* wall, const float* bc1,
+                           const float* bf, const float* vreg, float creg, const float* anchors, int B, int N, int S,
+                           float* dir, float* inv, float* anc_w, float* scratch, cudaStream_t stream);
+
+/* confi head (pointtransformer_seg.py:145,184-189). W0c [K*4][2][8][128][4]: per marker group and K-quarter a [128 x 32] slice. */
+int etch_conf_head_tc(const float* x, const float* logits, const float* W0c, const float* b0, const float* w2, const float* b2,
+                      int n, int K, float* conf, cudaStream_t stream);
+
+/* etch_linear on tcgen05, weight-stationary. Wc [NG][2][Kpad/4][NB][4], Kpad = 32*ceil(ci/32), NG = ceil(co/NB). */
+int etch_linear_tc(const float* X, int ldx, const float* Wc, int NB, int n, int ci, int co, const float* scale, const float* shift,
+                   const float* R, const float* seg, const int* seg_off, int nseg, int relu, float* Y, int ldy,
+                   cudaStream_t stream);
+
+/* etch_lm_fit plus SM-clock totals per (scan, phase) in prof (profiling aid for tools/microbench.py). */
+int etch_lm_fit_profile(const float* markers, const unsigned char* valid, const float* Tm, const float* Sm, const float* Pm,
+                        const float* Wm, const float* Jt, const float* Js, const int* parents, const unsigned* ancmask, int B,
+                        int M, int steps0, int steps1, float step0, float step1, float damp0, float damp1, float* params,
+                        int* iters, float* errs, long long* prof, cudaStream_t stream);
+
+/* tcgen05 building-block self test: C[128,N] = A[128,K] B[N,K]^T (3xTF32); and issue/copy latency probe (tests/, tools/). */
+int etch_umma_selftest(const float* A, const float* B, float* C, int K, int N, cudaStream_t stream);
+int etch_umma_latency(const float* src, long long* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
