@@ -41,6 +41,10 @@ static inline int etch_opt_n_threads(int work_size) {
     return t;
 }
 
+// SMs the persistent (1 CTA/SM) kernels may fill; 148 on B200 unless etch_set_sm_budget lowered it so that a concurrent
+// small-grid kernel of another stream (the LM fit of the previous batch) keeps its SMs.  Defined in index.cu.
+int etch_sm_budget();
+
 // 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned
 __device__ __forceinline__ void etch_ldg256(const float* p, float (&v)[8]) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

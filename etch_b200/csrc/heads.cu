@@ -360,7 +360,7 @@ ETCH_API int etch_direction_head(const float* feats, const int* up_idx, const fl
     static_assert(TOK * LDQ >= 128 * LDT, "hidden buffer must fit the QKV region");
     ETCH_TRY(cudaFuncSetAttribute(direction_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (N + 1) / 2;
-    int gx = 148 / B;  // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
+    int gx = etch_sm_budget() / B;  // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
     dim3 grid(gx, B);

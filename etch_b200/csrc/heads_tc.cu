@@ -153,7 +153,7 @@ ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float*
     const size_t smem = (size_t)2 * 128 * CT_K * 4 + (size_t)4 * CT_N * CT_KQ * 4 + 128;
     ETCH_TRY(cudaFuncSetAttribute(conf_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = etch_cdiv(n, 128);
-    if (grid > 148) grid = 148;
+    if (grid > etch_sm_budget()) grid = etch_sm_budget();
     conf_head_tc_kernel<<<grid, 256, smem, stream>>>(x, logits, W0c, b0, w2, b2, n, K, conf);
     ETCH_RETURN_LAST();
 }
@@ -556,7 +556,7 @@ ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const
     const size_t smem = (size_t)4 * DH_XB + (size_t)4 * DH_WB + (size_t)(2 * DH_NA * DH_LDKV + 256 + 128 + DH_NA * 9) * 4 + 128;
     ETCH_TRY(cudaFuncSetAttribute(direction_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (N + 1) / 2;
-    int gx = 148 / B;   // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
+    int gx = etch_sm_budget() / B;   // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
     dim3 grid(gx, B);

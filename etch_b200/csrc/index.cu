@@ -398,7 +398,17 @@ __global__ void __launch_bounds__(KNNW_WARPS * 32) knn_warp_kernel(int m, const 
 
 }  // namespace
 
+static int g_sm_budget = 148;
+int etch_sm_budget() { return g_sm_budget; }
+
 // ================================================================================================ C ABI
+// number of SMs the persistent kernels size their grids for (default 148 = all of a B200)
+ETCH_API int etch_set_sm_budget(int sms) {
+    if (sms < 1 || sms > 148) return ETCH_EINVAL;
+    g_sm_budget = sms;
+    return ETCH_OK;
+}
+
 // replaces epn_grouping.furthest_point_sampling (external/vgtk/vgtk/cuda/grouping_cuda.cpp:160-174)
 ETCH_API int etch_fps_bcn(const float* xyz, int B, int n, int m, int* idx, cudaStream_t stream) {
     if (!xyz || !idx || B <= 0 || n <= 0 || m < 0 || n > 28672) return ETCH_EINVAL;

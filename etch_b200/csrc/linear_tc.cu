@@ -43,29 +43,40 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
     const int frow = tid >> 1, fhalf = tid & 1;
     bool w_ready = false;
 
+    // X[m0 + frow, kc*32 + fhalf*16 .. +16) -> 4 float4 registers (zero beyond n / ci); issued one chunk ahead of its use so
+    // the global-load latency overlaps the barrier, the MMA issue and the ring wait of the current chunk
+    auto load_chunk = [&](int tile, int kc, float4 (&v)[4]) {
+        const int gm_row = tile * 128 + frow;
+        const int k0 = kc * 32 + fhalf * 16;
+        const float* src = X + (size_t)(gm_row < n ? gm_row : 0) * ldx + k0;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int k = k0 + c4 * 4;
+            v[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gm_row < n) {
+                if (k + 3 < ci && ((reinterpret_cast<uintptr_t>(src + c4 * 4) & 15) == 0)) v[c4] = __ldg(reinterpret_cast<const float4*>(src + c4 * 4));
+                else {
+                    if (k < ci) v[c4].x = __ldg(src + c4 * 4);
+                    if (k + 1 < ci) v[c4].y = __ldg(src + c4 * 4 + 1);
+                    if (k + 2 < ci) v[c4].z = __ldg(src + c4 * 4 + 2);
+                    if (k + 3 < ci) v[c4].w = __ldg(src + c4 * 4 + 3);
+                }
+            }
+        }
+    };
+    float4 xv[4];
+    if (blockIdx.x * 128 < n) load_chunk(blockIdx.x, 0, xv);
+
     for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
         const int m0 = tile * 128;
         for (int kc = 0; kc < nchunks; ++kc) {
             const uint32_t abuf = ga & 1;
             if (ga >= 2) umma::mbar_wait(&a_free[abuf], ((ga - 2) >> 1) & 1);
-            {   // stage X[m0:m0+128, kc*32:(kc+1)*32]: 2 threads per row, 16 floats each
-                const int gm_row = m0 + frow;
-                const int k0 = kc * 32 + fhalf * 16;
-                const float* src = X + (size_t)(gm_row < n ? gm_row : 0) * ldx + k0;
+            {   // split + store the staged chunk: 2 threads per row, 16 floats each
                 unsigned char* dh = s_A + abuf * 2 * LT_A;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
-                    const int k = k0 + c4 * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (gm_row < n) {
-                        if (k + 3 < ci && ((reinterpret_cast<uintptr_t>(src + c4 * 4) & 15) == 0)) v = __ldg(reinterpret_cast<const float4*>(src + c4 * 4));
-                        else {
-                            if (k < ci) v.x = __ldg(src + c4 * 4);
-                            if (k + 1 < ci) v.y = __ldg(src + c4 * 4 + 1);
-                            if (k + 2 < ci) v.z = __ldg(src + c4 * 4 + 2);
-                            if (k + 3 < ci) v.w = __ldg(src + c4 * 4 + 3);
-                        }
-                    }
+                    const float4 v = xv[c4];
                     float4 h, l;
                     umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
                     umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
@@ -73,6 +84,11 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
                     *reinterpret_cast<float4*>(dh + kq * (128 * 16) + frow * 16) = h;
                     *reinterpret_cast<float4*>(dh + LT_A + kq * (128 * 16) + frow * 16) = l;
                 }
+            }
+            {   // prefetch the next chunk (of this tile or of the next one)
+                int nt = tile, nk = kc + 1;
+                if (nk == nchunks) { nk = 0; nt = tile + gridDim.x; }
+                if (nt * 128 < n) load_chunk(nt, nk, xv);
             }
             umma::fence_async_smem();
             __syncthreads();
@@ -158,7 +174,7 @@ ETCH_API int etch_linear_tc(const float* X, int ldx, const float* Wc, int NB, in
     while (tcols < NB) tcols <<= 1;
     ETCH_TRY(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (n + 127) / 128;
-    int gx = 148 / NG;
+    int gx = etch_sm_budget() / NG;
     if (gx < 1) gx = 1;
     if (gx > ntiles) gx = ntiles;
     dim3 grid(gx, NG);

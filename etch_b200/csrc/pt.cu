@@ -404,7 +404,7 @@ ETCH_API int etch_pt_attention(const float* p, const float* qkv, const int* idx,
     const size_t smem = ((size_t)T * c + (size_t)T * T + (size_t)16 * T + c + 64 + 16) * 4;
     int grid = n;
     const int per_sm = smem > 110 * 1024 ? 1 : (smem > 50 * 1024 ? 2 : 4);
-    if (grid > 148 * per_sm) grid = 148 * per_sm;
+    if (grid > etch_sm_budget() * per_sm) grid = etch_sm_budget() * per_sm;
 #define ATT(R)                                                                                                   \
     {                                                                                                            \
         auto kern = pt_attn_kernel<R>;                                                                           \

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256, 1) inter_conv_tc_kernel(
 }
 
 int grid_for_tc(int ntiles, int B) {
-    int g = 148 / B;   // one wave of persistent CTAs (1 CTA/SM)
+    int g = etch_sm_budget() / B;   // one wave of persistent CTAs (1 CTA/SM)
     if (g < 1) g = 1;
     return ntiles < g ? ntiles : g;
 }

@@ -52,6 +52,10 @@ int etch_knn_packed(int m, int nsample, const float* xyz, const float* new_xyz, 
 /* block-size rule of the reference launchers (grouping_cuda_kernel.cu:29-33): 2^floor(log2 n) capped at 1024 */
 int etch_opt_threads(int work_size);
 
+/* Number of SMs the persistent (one CTA per SM) kernels size their grids for; default 148.  The pipelined runtime lowers it by
+ * the batch size so the LM fit of the previous batch (one CTA per scan, another stream) keeps its SMs. */
+int etch_set_sm_budget(int sms);
+
 /* ---- fused operators behind the Python operator API (boundary B1: models.models_pointcloud / models.fit_SMPL) ---- */
 /* Encoder features are point-major: feat [B, P, 60, C].  `stats` buffers are [B][C][2] doubles (sum, sum of squares),
  * zeroed by the caller, accumulated by the producer and consumed (as InstanceNorm mean / rstd) by the next kernel.   */
