@@ -125,3 +125,83 @@ ETCH_API int etch_umma_selftest(const float* A, const float* B, float* C, int K,
     umma_selftest_kernel<<<1, 128, smem, stream>>>(A, B, C, K, N);
     ETCH_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-level mma.sync (m16n8k8 TF32) issue-rate probe: every warp runs `iters` rounds of 8 independent accumulator
+// chains; out[cta] = SM cycles of the CTA.  Used to size the per-(point, anchor) neighbour contraction of the inter conv.
+namespace {
+__global__ void __launch_bounds__(1024) mma_sync_rate_kernel(long long* __restrict__ out, int iters, float seed) {
+    float c[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f; }
+    uint32_t a[4], b[2];
+    a[0] = __float_as_uint(seed + threadIdx.x); a[1] = a[0] ^ 0x100; a[2] = a[0] ^ 0x200; a[3] = a[0] ^ 0x300;
+    b[0] = a[0] ^ 0x400; b[1] = a[0] ^ 0x500;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1] + c[j][2] + c[j][3];
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    if (s == 123.456f) out[blockIdx.x] = 0;
+}
+}  // namespace
+
+ETCH_API int etch_mma_sync_rate(long long* out, int ctas, int warps, int iters, cudaStream_t stream) {
+    if (!out || ctas <= 0 || warps <= 0 || warps > 32 || iters <= 0) return ETCH_EINVAL;
+    mma_sync_rate_kernel<<<ctas, warps * 32, 0, stream>>>(out, iters, 1.0f);
+    ETCH_RETURN_LAST();
+}
+
+// FP32 issue-rate probe: mode 0 = scalar FFMA (16 independent chains), mode 1 = packed fma.rn.f32x2 (16 chains of 2)
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(1024) ffma_rate_kernel(long long* __restrict__ out, int iters, float seed) {
+    float x = seed + threadIdx.x * 1e-3f, y = 1.0f - x * 1e-3f;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = j * 0.5f;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fmaf(acc[j], x, y);
+        } else {
+            unsigned long long xx, yy;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x), "f"(x));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(yy) : "f"(y), "f"(y));
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                unsigned long long a;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc[j]), "f"(acc[j + 1]));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(xx), "l"(yy));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[j]), "=f"(acc[j + 1]) : "l"(a));
+            }
+        }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += acc[j];
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    if (s == 123.456f) out[blockIdx.x] = 0;
+}
+}  // namespace
+
+ETCH_API int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int mode, cudaStream_t stream) {
+    if (!out || ctas <= 0 || warps <= 0 || warps > 32 || iters <= 0) return ETCH_EINVAL;
+    if (mode == 0) ffma_rate_kernel<0><<<ctas, warps * 32, 0, stream>>>(out, iters, 1.0f);
+    else ffma_rate_kernel<1><<<ctas, warps * 32, 0, stream>>>(out, iters, 1.0f);
+    ETCH_RETURN_LAST();
+}

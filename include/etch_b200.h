@@ -194,6 +194,10 @@ int etch_lm_fit_profile(const float* markers, const unsigned char* valid, const 
 /* tcgen05 building-block self test: C[128,N] = A[128,K] B[N,K]^T (3xTF32); and issue/copy latency probe (tests/, tools/). */
 int etch_umma_selftest(const float* A, const float* B, float* C, int K, int N, cudaStream_t stream);
 int etch_umma_latency(const float* src, long long* out, cudaStream_t stream);
+/* probe: SM cycles for `iters` x 8 warp-level mma.sync.m16n8k8 TF32 per warp, `warps` warps per CTA; out[ctas] */
+int etch_mma_sync_rate(long long* out, int ctas, int warps, int iters, cudaStream_t stream);
+/* probe: SM cycles for `iters` x 32 FP32 FMAs per thread; mode 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
+int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int mode, cudaStream_t stream);
 
 #ifdef __cplusplus
 }
