@@ -298,7 +298,7 @@ def run_etch(args, rank, world, local_rank):
     total_kernel_ms = sum(t for _, t in prof.values())
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     def _algo(name):
-        return ALGO_GFLOP_5K.get(name, ALGO_GFLOP_5K.get(name[:-3] if name.endswith("_tc") else name))
+        return ALGO_GFLOP_5K.get(name, ALGO_GFLOP_5K.get(name[:-3] if name.endswith(("_tc", "_v3")) else name))
     # dominant kernel = the most expensive one that has a stated algorithmic-work figure (all the big ones do)
     dom, (dom_calls, dom_ms) = next(((k, v) for k, v in top if _algo(k) is not None), top[0])
     scale = N / 5000.0

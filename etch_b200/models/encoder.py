@@ -14,6 +14,9 @@ from . import spec, tc
 
 # tensor-core (tcgen05) kernels for the dense-GEMM stages; ETCH_B200_NO_TC=1 selects the fp32 CUDA-core versions (A/B tests)
 USE_TC = os.environ.get("ETCH_B200_NO_TC", "0") != "1"
+# InterSO3Conv variant: "v3" (one point per tile, TMA-fed, TMEM-parked accumulators: the product path) or "v2" (the
+# 2-point slab kernel etch_so3_inter_conv_tc, kept for A/B runs)
+INTER_VARIANT = os.environ.get("ETCH_B200_INTER", "v3")
 
 
 def to_reference_layout(feats_bpac):
@@ -30,6 +33,22 @@ def _inter_slabs(W, ci, co):
         c0, h = (sl // 2) * 8, sl % 2
         blk = W3[:, c0:c0 + 8, h * 12:(h + 1) * 12].reshape(co, 8, 2, 6).permute(0, 2, 1, 3).reshape(co, 96)  # [o][kgl][c][i]
         slabs.append(tc.tc_operand(blk.contiguous(), "cpu"))
+    return torch.stack(slabs, 0).contiguous()
+
+
+def _inter_slabs_v3(W, ci, co):
+    """BasicSO3Conv weight [co, ci*24] -> [ci/32*16, 12, 2*co, 4] for etch_so3_inter_conv_v3: per (pass, channel slot cc,
+    kernel-point half hh) the 48-column slab K'' = o*12 + i <-> W[:, (32*pass + 8*o + cc)*24 + 12*hh + i]; rows are
+    [W_hi; W_lo] (TF32 split) so that one MMA with N = 2*co forms A_hi*W_hi and A_hi*W_lo; canonical K-major tiles."""
+    W3 = W.view(co, ci, 24)
+    slabs = []
+    for ps in range(ci // 32):
+        for cc in range(8):
+            for hh in range(2):
+                chans = [32 * ps + 8 * o + cc for o in range(4)]
+                blk = W3[:, chans, 12 * hh:12 * hh + 12].reshape(co, 48).contiguous()
+                hi, lo = tc.split_tf32(blk)
+                slabs.append(tc.canonical(torch.cat([hi, lo], 0)))
     return torch.stack(slabs, 0).contiguous()
 
 
@@ -63,6 +82,7 @@ class EncoderPlan:
                 # tensor-core operands: per anchor-neighbour slot j the [c_out x c] slice, TF32-split, canonical tiles
                 Wc_intra=torch.stack([tc.tc_operand(Wi.view(co, co, 12)[:, :, j].cpu(), "cpu") for j in range(12)], 0).contiguous().to(device),
                 Wc_inter=(_inter_slabs(W.cpu(), ci, co).to(device) if ci > 1 else None),
+                Wc_inter3=(_inter_slabs_v3(W.cpu(), ci, co).to(device) if ci > 1 else None),
                 Wc_skip=(tc.tc_operand(sd[pre + "skip_conv.weight"].view(co, ci).cpu(), device)[None].contiguous() if ci > 1 else None),
                 b_skip=sd[pre + "skip_conv.bias"].to(**f32).contiguous(),
             )
@@ -96,6 +116,10 @@ def run_encoder(plan, xyz_bcn, trace=None):
         if ci == 1:
             L.call("so3_inter_conv_c1", L.ptr(xyz), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["kr"]), L.ptr(lp["Wt_inter"]),
                    L.ptr(lp["b_inter"]), B, q, P, nn_, co, L.f32(lp["sigma"]), L.ptr(z1), L.ptr(stats[0]))
+        elif USE_TC and INTER_VARIANT == "v3":
+            g4 = torch.empty(B, P, nn_, 4, dtype=torch.float32, device=dev)
+            L.call("so3_inter_conv_v3", L.ptr(xyz), L.ptr(feats), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["krs"]), L.ptr(lp["Wc_inter3"]),
+                   L.ptr(lp["b_inter"]), B, q, P, nn_, ci, co, L.f32(lp["sigma"]), L.ptr(g4), L.ptr(z1), L.ptr(stats[0]))
         else:
             L.call("so3_inter_conv_tc" if USE_TC else "so3_inter_conv", L.ptr(xyz), L.ptr(feats), L.ptr(sidx), L.ptr(nbr), L.ptr(lp["krs"]),
                    L.ptr(lp["Wc_inter"] if USE_TC else lp["Wt_inter"]), L.ptr(lp["b_inter"]), B, q, P, nn_, ci, co, L.f32(lp["sigma"]),

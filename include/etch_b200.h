@@ -161,6 +161,15 @@ int etch_so3_inter_conv_tc(const float* xyz, const float* feat, const int* sampl
                            const float* Wc, const float* bias, int B, int q, int P, int nn, int cin, int cout, float sigma,
                            float* zraw, double* stats, cudaStream_t stream);
 
+/* InterSO3Conv, one point per tile (the product path; replaces etch_so3_inter_conv_tc, which stays as an A/B reference):
+ * neighbour rows by 2-D tiled TMA, contraction over the neighbours on the FP32 pipes with 96 accumulators per thread,
+ * accumulators parked in TMEM and fed slab by slab to tcgen05 for the channel mixing.  Wc [cin/32*16][12][2*cout][4]: per
+ * (pass, channel slot cc, kernel-point half hh) the 48-column slab K'' = o*12 + i <-> W[.][(32*pass + 8*o + cc)*24 + 12*hh + i],
+ * rows [W_hi; W_lo].  g4: caller-owned scratch [B,P,nn,4] fp32 (relative neighbour positions, written by a pre-pass). */
+int etch_so3_inter_conv_v3(const float* xyz, const float* feat, const int* sample_idx, const int* nbr, const float* krs,
+                           const float* Wc, const float* bias, int B, int q, int P, int nn, int cin, int cout, float sigma,
+                           float* g4, float* zraw, double* stats, cudaStream_t stream);
+
 /* IntraSO3Conv (functional.py:331-343, modules.py:131-153). Wc [12][2][c/4][cout][4]. */
 int etch_so3_intra_conv_tc(const float* zin, const double* in_stats, const int* intra_idx, const float* Wc, const float* bias,
                            int B, int P, int c, int cout, float* zraw, double* stats, cudaStream_t stream);
