@@ -28,7 +28,12 @@ namespace {
 constexpr int NA = 60;
 constexpr int NK = 24;
 constexpr int NPAIRS = NA * NK;              // 1440 (anchor, kernel point) pairs
-constexpr int NB = 2;                        // neighbours per chunk
+#ifndef V3_SLEEP
+#define V3_SLEEP 256
+#endif
+#ifndef V3_SMEM_CAP
+#define V3_SMEM_CAP 227
+#endif
 constexpr int NBR_SLOT = 8192;               // one neighbour tile: 60 rows x 128 B, padded to the 1 KB swizzle atom
 constexpr int NBR_TX = NA * 128;             // bytes one TMA box delivers
 constexpr int CT = 480;                      // compute threads (15 warps)
@@ -38,15 +43,18 @@ constexpr int NSLAB = 16;                    // slabs per pass: 8 channel slots 
 constexpr int A_LBO = 1056;                  // K-chunk stride of the A slab (64 rows x 16 B + 32 B: conflict-free stores)
 constexpr int A_HALF = (SLAB_K / 4) * A_LBO; // one (hi or lo) A slab
 constexpr int A_SLOT = 2 * A_HALF;
-constexpr int RING = 3;                      // neighbour-chunk ring depth
 constexpr int GRING = 4;                     // per-point geometry ring depth
 constexpr int PARK_COL = 128;                // TMEM: [0, 2*c_out) accumulator, [128, 512) parked T
 
 template <int CIN, int COUT, int NN>
 struct V3Cfg {
+    // neighbours per chunk / chunk-ring depth: 4 x 2 where the shared-memory budget allows it (c_out = 32), else 2 x 3
+    static constexpr int NB = COUT == 32 ? 4 : 2;
+    static constexpr int RING = COUT == 32 ? 2 : 3;
     static constexpr int NPASS = CIN / 32;
     static constexpr int NCHUNK = NN / NB;
-    static constexpr int SLAB_EVERY = NCHUNK / NSLAB;
+    static constexpr int SLAB_EVERY = NCHUNK >= NSLAB ? NCHUNK / NSLAB : 1;   // a slab group every SLAB_EVERY chunks ...
+    static constexpr int SLAB_GROUP = NCHUNK >= NSLAB ? 1 : NSLAB / NCHUNK;   // ... of SLAB_GROUP slabs
     static constexpr uint32_t F_BYTES = RING * NB * NBR_SLOT;
     static constexpr uint32_t W_BYTES = 2 * NB * NPAIRS * 4;
     static constexpr uint32_t A_BYTES = 2 * A_SLOT;
@@ -57,10 +65,16 @@ struct V3Cfg {
     static constexpr uint32_t NBR_BYTES = GRING * NN * 4;
     static constexpr uint32_t STAT_BYTES = COUT * 16;
     static constexpr size_t smem = 1024 + F_BYTES + W_BYTES + A_BYTES + 2 * WSLAB + KRS_BYTES + Z_BYTES + G_BYTES + NBR_BYTES + STAT_BYTES;
-    static_assert(NCHUNK % NSLAB == 0, "one slab every SLAB_EVERY chunks");
-    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static_assert(SLAB_GROUP * (NCHUNK / SLAB_EVERY) == NSLAB, "slab schedule covers a pass");
+    static_assert(smem <= V3_SMEM_CAP * 1024, "shared memory budget");
     static_assert(2 * COUT <= PARK_COL, "accumulator columns");
 };
+
+// fp32 -> (hi, lo), hi = x rounded to TF32 (ties away; the integer form of cvt.rna without its NaN/Inf special cases), lo = x - hi
+__device__ __forceinline__ void split_fast(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
 
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
     float* __restrict__ zraw, double* __restrict__ stats)
 {
     using Cfg = V3Cfg<CIN, COUT, NN>;
-    constexpr int NPASS = Cfg::NPASS, NCHUNK = Cfg::NCHUNK, SLAB_EVERY = Cfg::SLAB_EVERY;
+    constexpr int NB = Cfg::NB, RING = Cfg::RING, NPASS = Cfg::NPASS, NCHUNK = Cfg::NCHUNK, SLAB_EVERY = Cfg::SLAB_EVERY, SLAB_GROUP = Cfg::SLAB_GROUP;
     constexpr uint32_t WSLAB = Cfg::WSLAB;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* base = smem_dyn + ((1024u - (umma::smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms need 1 KB alignment
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                     progressed = true;
                 }
             }
-            if (!progressed) __nanosleep(64);   // do not steal issue slots from the compute warps of this scheduler
+            if (!progressed) __nanosleep(V3_SLEEP);   // do not steal issue slots from the compute warps of this scheduler
         }
     } else {
         // =========================== compute warps ===========================
@@ -269,8 +283,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
 #pragma unroll
                     for (int j4 = 0; j4 < 3; ++j4) {
                         float4 hi, lo;
-                        umma::split_tf32(v[j4 * 4 + 0], hi.x, lo.x); umma::split_tf32(v[j4 * 4 + 1], hi.y, lo.y);
-                        umma::split_tf32(v[j4 * 4 + 2], hi.z, lo.z); umma::split_tf32(v[j4 * 4 + 3], hi.w, lo.w);
+                        split_fast(v[j4 * 4 + 0], hi.x, lo.x); split_fast(v[j4 * 4 + 1], hi.y, lo.y);
+                        split_fast(v[j4 * 4 + 2], hi.z, lo.z); split_fast(v[j4 * 4 + 3], hi.w, lo.w);
                         *reinterpret_cast<float4*>(dh + j4 * A_LBO) = hi;
                         *reinterpret_cast<float4*>(dh + A_HALF + j4 * A_LBO) = lo;
                     }
@@ -333,7 +347,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                     bar_sync_named(1, CT);
                     if (gc + 1 < total_chunks) wgen(gc + 1);
                 }
-                if (parked && (c % SLAB_EVERY) == 0) slab_step((uint32_t)c / SLAB_EVERY);
+                if (parked && (c % SLAB_EVERY) == 0) {
+#pragma unroll
+                    for (int sg = 0; sg < SLAB_GROUP; ++sg) slab_step((uint32_t)(c / SLAB_EVERY) * SLAB_GROUP + sg);
+                }
                 if (work) {
                     const uint32_t sl = gc % RING;
                     umma::mbar_wait(&f_full[sl], (gc / RING) & 1);

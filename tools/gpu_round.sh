@@ -5,10 +5,10 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $OUT/gpu.txt 2>&1
 if [ -z "$SKIP_TESTS" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
+  timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
   tail -5 $OUT/pytest.log
 fi
-timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
+timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 $BENCH_ARGS > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
 tail -c 600 $OUT/bench.err
 python -c "
 import json;d=json.loads(open('$OUT/bench.json').read().strip().splitlines()[-1])
