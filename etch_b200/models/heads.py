@@ -16,6 +16,7 @@ from .spec import PT_BLOCKS, PT_NSAMPLE, PT_STRIDE
 
 EPS_BN = 1e-5
 USE_TC = os.environ.get("ETCH_B200_NO_TC", "0") != "1"  # tcgen05 kernels (default) vs fp32 CUDA-core versions
+PT_ATTN_TC = os.environ.get("ETCH_B200_PT_ATTN", "tc") == "tc"  # vector attention: tensor-core tiles (default) or the CTA-per-point kernel
 
 
 # ----------------------------------------------------------------------------- direction head
@@ -118,6 +119,15 @@ class _Block:
         self.W3t = _wt(sd[pre + "linear3.weight"], d)
         self.s3, self.h3 = _fold_bn(sd, pre + "bn3.", d)
         self.c = self.W1t.shape[0]
+        # tensor-core attention (etch_pt_attention_tc): per-channel constants packed [c][8] and W1 as (hi, lo) canonical tiles
+        # per 64-channel chunk, rows padded to the UMMA N granularity
+        c = self.Wa.shape[1]
+        T = self.Wa.shape[0]
+        tp = max(T, 16)
+        self.chan = torch.cat([self.P3, self.p3b[:, None], self.s0[:, None], self.h0[:, None], self.so[:, None], self.ho[:, None]], 1).contiguous()
+        wa = torch.zeros(tp, c)
+        wa[:T] = self.Wa.detach().float().cpu()
+        self.Wa_c = torch.stack([tc.tc_operand(wa[:, k:k + 64].contiguous(), "cpu") for k in range(0, c, 64)], 0).contiguous().to(d["device"])
 
 
 class PTPlan:
@@ -246,9 +256,13 @@ def _block(blk, geo, lvl, x):
     qkv = _linear(y, blk.Wqkv, None, blk.bqkv)
     a = torch.empty(n, c, dtype=torch.float32, device=x.device)
     idx = geo.knn_self[lvl][0]
-    L.call("pt_attention", L.ptr(geo.p[lvl]), L.ptr(qkv), L.ptr(idx), L.ptr(blk.P0), L.ptr(blk.p0b), L.ptr(blk.P3), L.ptr(blk.p3b),
-           L.ptr(blk.s0), L.ptr(blk.h0), L.ptr(blk.Wa), L.ptr(blk.ba), L.ptr(blk.Wb), L.ptr(blk.bb), L.ptr(blk.so), L.ptr(blk.ho),
-           n, int(idx.shape[1]), c, L.ptr(a))
+    if USE_TC and PT_ATTN_TC:
+        L.call("pt_attention_tc", L.ptr(geo.p[lvl]), L.ptr(qkv), L.ptr(idx), L.ptr(blk.P0), L.ptr(blk.p0b), L.ptr(blk.chan), L.ptr(blk.Wa_c),
+               L.ptr(blk.ba), L.ptr(blk.Wb), L.ptr(blk.bb), n, int(idx.shape[1]), c, L.ptr(a))
+    else:
+        L.call("pt_attention", L.ptr(geo.p[lvl]), L.ptr(qkv), L.ptr(idx), L.ptr(blk.P0), L.ptr(blk.p0b), L.ptr(blk.P3), L.ptr(blk.p3b),
+               L.ptr(blk.s0), L.ptr(blk.h0), L.ptr(blk.Wa), L.ptr(blk.ba), L.ptr(blk.Wb), L.ptr(blk.bb), L.ptr(blk.so), L.ptr(blk.ho),
+               n, int(idx.shape[1]), c, L.ptr(a))
     return _linear(a, blk.W3t, blk.s3, blk.h3, R=x, relu=True)
 
 

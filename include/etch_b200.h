@@ -170,6 +170,13 @@ int etch_so3_inter_conv_v3(const float* xyz, const float* feat, const int* sampl
                            const float* Wc, const float* bias, int B, int q, int P, int nn, int cin, int cout, float sigma,
                            float* g4, float* zraw, double* stats, cudaStream_t stream);
 
+/* PointTransformerLayer (pointtransformer_seg.py:8-37) + bn2 + ReLU with the first attention linear as a GEMM over
+ * (point, neighbour) rows on tcgen05.  chan [c][8] = {P3 row (3), p3b, s0, h0, so, ho}; W1c [c/64][2][16][max(c/8,16)][4]
+ * (TF32 hi/lo canonical tiles of the BN-folded Linear(c, c/8), one per 64-channel chunk); ns in {8, 16}. */
+int etch_pt_attention_tc(const float* p, const float* qkv, const int* idx, const float* P0, const float* p0b, const float* chan,
+                         const float* W1c, const float* b1, const float* W2, const float* b2, int n, int ns, int c, float* out,
+                         cudaStream_t stream);
+
 /* IntraSO3Conv (functional.py:331-343, modules.py:131-153). Wc [12][2][c/4][cout][4]. */
 int etch_so3_intra_conv_tc(const float* zin, const double* in_stats, const int* intra_idx, const float* Wc, const float* bias,
                            int B, int P, int c, int cout, float* zraw, double* stats, cudaStream_t stream);
