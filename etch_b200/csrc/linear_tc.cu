@@ -24,11 +24,17 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* s_A = smem_raw;                 // [2 buffers][hi|lo]
     unsigned char* s_W = s_A + 4 * LT_A;           // [hi|lo] [Kpad/4][NB][4]
+    __shared__ __align__(16) float s_scale[256], s_shift[256];   // folded BatchNorm of this CTA's NB columns (1, 0 when absent)
     __shared__ uint64_t a_free[2], w_full, acc_full;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp_col0 = blockIdx.y * NB;
     const uint32_t W_BYTES = (uint32_t)NB * Kpad * 4;     // one (hi or lo) tile
+    for (int i = tid; i < NB; i += 256) {
+        const int gc = blockIdx.y * NB + i;
+        s_scale[i] = (scale && gc < co) ? __ldg(scale + gc) : 1.0f;
+        s_shift[i] = (shift && gc < co) ? __ldg(shift + gc) : 0.0f;
+    }
     if (warp == 0) umma::tmem_alloc(&tmem_base, tcols);
     if (tid == 0) { umma::mbar_init(&a_free[0], 1); umma::mbar_init(&a_free[1], 1); umma::mbar_init(&w_full, 1); umma::mbar_init(&acc_full, 1); }
     umma::fence_before_sync();
@@ -64,46 +70,51 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
             }
         }
     };
-    float4 xv[4];
-    if (blockIdx.x * 128 < n) load_chunk(blockIdx.x, 0, xv);
+    // The (tile, K-chunk) pairs of this CTA form one sequence g = 0 .. G-1; PF chunks of X are always in flight in registers
+    // (each register set is refilled with chunk g + PF right after chunk g has been split into the A ring), so the L2 / HBM
+    // latency of a row tile is hidden behind PF chunk steps instead of one.
+    constexpr int PF = 3;
+    const int my_tiles = (int)blockIdx.x * 128 < n ? ((n + 127) / 128 - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int G = my_tiles * nchunks;
+    float4 xv0[4], xv1[4], xv2[4];
+    auto prefetch = [&](int g, float4 (&v)[4]) {
+        if (g < G) load_chunk((int)blockIdx.x + (g / nchunks) * (int)gridDim.x, g % nchunks, v);
+    };
+    prefetch(0, xv0); prefetch(1, xv1); prefetch(2, xv2);
 
-    for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
+    auto step = [&](int g, float4 (&xv)[4]) {
+        const int tile = (int)blockIdx.x + (g / nchunks) * (int)gridDim.x, kc = g % nchunks;
         const int m0 = tile * 128;
-        for (int kc = 0; kc < nchunks; ++kc) {
-            const uint32_t abuf = ga & 1;
-            if (ga >= 2) umma::mbar_wait(&a_free[abuf], ((ga - 2) >> 1) & 1);
-            {   // split + store the staged chunk: 2 threads per row, 16 floats each
-                unsigned char* dh = s_A + abuf * 2 * LT_A;
+        const uint32_t abuf = ga & 1;
+        if (ga >= 2) umma::mbar_wait(&a_free[abuf], ((ga - 2) >> 1) & 1);
+        {   // split + store the staged chunk: 2 threads per row, 16 floats each
+            unsigned char* dh = s_A + abuf * 2 * LT_A;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 v = xv[c4];
-                    float4 h, l;
-                    umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
-                    umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
-                    const int kq = fhalf * 4 + c4;
-                    *reinterpret_cast<float4*>(dh + kq * (128 * 16) + frow * 16) = h;
-                    *reinterpret_cast<float4*>(dh + LT_A + kq * (128 * 16) + frow * 16) = l;
-                }
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 v = xv[c4];
+                float4 h, l;
+                umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+                umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+                const int kq = fhalf * 4 + c4;
+                *reinterpret_cast<float4*>(dh + kq * (128 * 16) + frow * 16) = h;
+                *reinterpret_cast<float4*>(dh + LT_A + kq * (128 * 16) + frow * 16) = l;
             }
-            {   // prefetch the next chunk (of this tile or of the next one)
-                int nt = tile, nk = kc + 1;
-                if (nk == nchunks) { nk = 0; nt = tile + gridDim.x; }
-                if (nt * 128 < n) load_chunk(nt, nk, xv);
-            }
-            umma::fence_async_smem();
-            __syncthreads();
-            if (warp == 0) {
-                if (!w_ready) { umma::mbar_wait(&w_full, 0); w_ready = true; }
-                umma::fence_after_sync();
-                const uint32_t a_hi = umma::smem_u32(s_A + abuf * 2 * LT_A), a_lo = a_hi + LT_A;
-                const uint32_t koff = (uint32_t)kc * 8 * NB * 16;     // 8 k-chunks of 4 floats, each NB*16 bytes
-                const uint32_t b_hi = umma::smem_u32(s_W) + koff, b_lo = b_hi + W_BYTES;
-                umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, 32, NB, kc > 0);
-                umma::commit(&a_free[abuf]);
-                if (kc == nchunks - 1) umma::commit(&acc_full);
-            }
-            ++ga;
         }
+        prefetch(g + PF, xv);
+        umma::fence_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            if (!w_ready) { umma::mbar_wait(&w_full, 0); w_ready = true; }
+            umma::fence_after_sync();
+            const uint32_t a_hi = umma::smem_u32(s_A + abuf * 2 * LT_A), a_lo = a_hi + LT_A;
+            const uint32_t koff = (uint32_t)kc * 8 * NB * 16;     // 8 k-chunks of 4 floats, each NB*16 bytes
+            const uint32_t b_hi = umma::smem_u32(s_W) + koff, b_lo = b_hi + W_BYTES;
+            umma::issue_gemm_3xtf32(tmem, a_hi, a_lo, b_hi, b_lo, 32, NB, kc > 0);
+            umma::commit(&a_free[abuf]);
+            if (kc == nchunks - 1) umma::commit(&acc_full);
+        }
+        ++ga;
+        if (kc != nchunks - 1) return;
         // ---- epilogue ----
         umma::mbar_wait(&acc_full, nacc & 1);
         ++nacc;
@@ -120,18 +131,35 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
                 umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c * 32, v);
                 if (gmr < n) {
                     const int gc0 = grp_col0 + c * 32;
+                    const bool full = gc0 + 32 <= co && c * 32 + 32 <= NB;
+                    if (seg) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int gc = gc0 + i;
-                        if (gc < co && c * 32 + i < NB) {
-                            float t = v[i];
-                            if (seg) t += __ldg(seg + (size_t)sb * co + gc);
-                            if (scale) t *= __ldg(scale + gc);
-                            if (shift) t += __ldg(shift + gc);
-                            if (R) t += __ldg(R + (size_t)gmr * co + gc);
-                            if (relu) t = fmaxf(t, 0.f);
-                            v[i] = t;
+                        for (int i = 0; i < 32; ++i)
+                            if (gc0 + i < co) v[i] += __ldg(seg + (size_t)sb * co + gc0 + i);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {   // folded BatchNorm from shared memory (warp-uniform addresses: broadcast)
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c * 32 + i), sh = *reinterpret_cast<const float4*>(s_shift + c * 32 + i);
+                        v[i] = fmaf(v[i], sc.x, sh.x); v[i + 1] = fmaf(v[i + 1], sc.y, sh.y);
+                        v[i + 2] = fmaf(v[i + 2], sc.z, sh.z); v[i + 3] = fmaf(v[i + 3], sc.w, sh.w);
+                    }
+                    if (R) {
+                        const float* rs = R + (size_t)gmr * co + gc0;
+                        if (full && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rs + i));
+                                v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (gc0 + i < co && c * 32 + i < NB) v[i] += __ldg(rs + i);
                         }
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     float* dst = Y + (size_t)gmr * ldy + gc0;
                     if (gc0 + 32 <= co && c * 32 + 32 <= NB && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -148,6 +176,12 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
         umma::fence_before_sync();
         __syncthreads();   // accumulator drained before the next tile's first MMA overwrites it
         umma::fence_after_sync();
+    };
+#pragma unroll 1
+    for (int g = 0; g < G; g += PF) {
+        step(g, xv0);
+        if (g + 1 < G) step(g + 1, xv1);
+        if (g + 2 < G) step(g + 2, xv2);
     }
     if (warp == 0 && !w_ready) {   // CTA had no tile: still drain the weight copies before exiting
         umma::mbar_wait(&w_full, 0);

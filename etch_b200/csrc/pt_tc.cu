@@ -43,10 +43,11 @@ struct PtCfg {
     static constexpr int TCOLS = TP <= 32 ? 32 : 64;
 };
 
-template <int C>
+template <int C, int NS>
 __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict__ p, const float* __restrict__ qkv,
-                                                         const int* __restrict__ idx, AttnTcW W, int n, int ns,
+                                                         const int* __restrict__ idx, AttnTcW W, int n,
                                                          float* __restrict__ out) {
+    constexpr int ns = NS;
     using Cfg = PtCfg<C>;
     constexpr int T = Cfg::T, TP = Cfg::TP, NCH = Cfg::NCH, LDL = Cfg::LDL;
     constexpr uint32_t W_BYTES = Cfg::W_BYTES;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict
                                         &w_full[(n_w + ch + 1) & 1]);
                 }
                 const int c0 = ch * PT_KC + half * 32;
-#pragma unroll 2
+#pragma unroll 4
                 for (int g = 0; g < 8; ++g) {
                     const float4 kv = __ldg(reinterpret_cast<const float4*>(krow + c0) + g);
                     const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow + c0) + g);
@@ -195,12 +196,16 @@ __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict
         for (int it = tid; it < ppt * T; it += 256) {
             const int pl = it / T, u = it % T;
             float* col = s_lg + (pl * ns) * LDL + u;
+            float lg[NS];
             float mx = -INFINITY;
-            for (int j = 0; j < ns; ++j) mx = fmaxf(mx, col[j * LDL]);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { lg[j] = col[j * LDL]; mx = fmaxf(mx, lg[j]); }
             float s = 0.f;
-            for (int j = 0; j < ns; ++j) { const float ev = expf(col[j * LDL] - mx); col[j * LDL] = ev; s += ev; }
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { lg[j] = expf(lg[j] - mx); s += lg[j]; }
             const float inv = 1.0f / s;
-            for (int j = 0; j < ns; ++j) col[j * LDL] *= inv;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) col[j * LDL] = lg[j] * inv;
         }
         __syncthreads();
         // ---- E. aggregation (v + p_r) * weight, channel-parallel; bn2 + ReLU epilogue ----
@@ -210,13 +215,16 @@ __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict
             if (i >= n) continue;
             const float4 ca = *reinterpret_cast<const float4*>(s_chan + chn * 8);
             const float4 cb = *reinterpret_cast<const float4*>(s_chan + chn * 8 + 4);
+            float vv[NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) vv[j] = __ldg(qkv + (size_t)s_nb[pl * NS + j] * 3 * C + 2 * C + chn);   // NS gathers in flight
             float acc = 0.f;
-            for (int j = 0; j < ns; ++j) {
-                const int r = pl * ns + j;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const int r = pl * NS + j;
                 const float4 ev = *reinterpret_cast<const float4*>(s_e + r * 4);
                 const float pr = fmaf(ca.z, ev.z, fmaf(ca.y, ev.y, fmaf(ca.x, ev.x, ca.w)));
-                const float vv = __ldg(qkv + (size_t)s_nb[r] * 3 * C + 2 * C + chn);
-                acc = fmaf(vv + pr, s_lg[r * LDL + (chn % T)], acc);
+                acc = fmaf(vv[j] + pr, s_lg[r * LDL + (chn % T)], acc);
             }
             out[(size_t)i * C + chn] = fmaxf(fmaf(acc, cb.z, cb.w), 0.f);
         }
@@ -227,18 +235,19 @@ __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict
     if (warp == 0) umma::tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
-template <int C>
-int launch_pt_attn_tc(const float* p, const float* qkv, const int* idx, const AttnTcW& W, int n, int ns, float* out, cudaStream_t stream) {
+template <int C, int NS>
+int launch_pt_attn_tc(const float* p, const float* qkv, const int* idx, const AttnTcW& W, int n, float* out, cudaStream_t stream) {
     using Cfg = PtCfg<C>;
+    constexpr int ns = NS;
     static_assert(Cfg::smem <= 227 * 1024, "shared memory budget");
-    auto kern = pt_attn_tc_kernel<C>;
+    auto kern = pt_attn_tc_kernel<C, NS>;
     ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
     const int ppt = PT_ROWS / ns;
     const int ntiles = (n + ppt - 1) / ppt;
     const int per_sm = Cfg::smem <= 110 * 1024 ? 2 : 1;
     int grid = etch_sm_budget() * per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, 256, Cfg::smem, stream>>>(p, qkv, idx, W, n, ns, out);
+    kern<<<grid, 256, Cfg::smem, stream>>>(p, qkv, idx, W, n, out);
     ETCH_RETURN_LAST();
 }
 
@@ -253,9 +262,8 @@ ETCH_API int etch_pt_attention_tc(const float* p, const float* qkv, const int* i
     if (!p || !qkv || !idx || !P0 || !p0b || !chan || !W1c || !b1 || !W2 || !b2 || !out || n <= 0) return ETCH_EINVAL;
     if (ns != 8 && ns != 16) return ETCH_EINVAL;
     AttnTcW W{P0, p0b, chan, W1c, b1, W2, b2};
-    if (c == 64) return launch_pt_attn_tc<64>(p, qkv, idx, W, n, ns, out, stream);
-    if (c == 128) return launch_pt_attn_tc<128>(p, qkv, idx, W, n, ns, out, stream);
-    if (c == 256) return launch_pt_attn_tc<256>(p, qkv, idx, W, n, ns, out, stream);
-    if (c == 512) return launch_pt_attn_tc<512>(p, qkv, idx, W, n, ns, out, stream);
+#define CASE(cc, nn) if (c == cc && ns == nn) return launch_pt_attn_tc<cc, nn>(p, qkv, idx, W, n, out, stream);
+    CASE(64, 8) CASE(64, 16) CASE(128, 8) CASE(128, 16) CASE(256, 8) CASE(256, 16) CASE(512, 8) CASE(512, 16)
+#undef CASE
     return ETCH_EINVAL;
 }
