@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     const float* __restrict__ bc1,     // [64]
     const float* __restrict__ bf,      // [128]
     const float* __restrict__ vreg,    // [128]
-    float creg, const float* __restrict__ anchors, int N, int S,
+    float creg, const float* __restrict__ anchors, int nscans, int N, int S,
     double* __restrict__ ce_out, float* __restrict__ anc_w)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     float* s_anc = s_w + 128;                              // [60][9]
     __shared__ uint64_t b_full[2], b_empty[2], bar_mma;
     __shared__ uint32_t tmem_base;
-    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < DH_NA * 9; i += 256) s_anc[i] = __ldg(anchors + i);
     if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
     if (tid == 0) {
@@ -374,10 +374,13 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     DhIssuer iss{wall, s_B, b_full, b_empty, 0u, 0u, 0};
     uint32_t n_mma = 0;
     const int ntiles = (N + 1) / 2;
-    const float* F = feats + (size_t)b * S * DH_NA * 64;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // scan-major tile sequence: the whole grid blends from one scan's coarse features at a time (19 MB, L2 resident) instead of
+    // all B of them (the scan-parallel grid re-read them 4x from DRAM)
+    for (int gt = blockIdx.x; gt < ntiles * nscans; gt += gridDim.x) {
+        const int b = gt / ntiles, tile = gt - b * ntiles;
+        const float* F = feats + (size_t)b * S * DH_NA * 64;
         const int p0 = tile * 2;
         if (warp == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
         // ---- 0. blend the three coarse rows into the token tile (hi/lo, canonical) ----
@@ -556,11 +559,9 @@ ETCH_API int etch_direction_head_tc(const float* feats, const int* up_idx, const
     const size_t smem = (size_t)4 * DH_XB + (size_t)4 * DH_WB + (size_t)(2 * DH_NA * DH_LDKV + 256 + 128 + DH_NA * 9) * 4 + 128;
     ETCH_TRY(cudaFuncSetAttribute(direction_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (N + 1) / 2;
-    int gx = etch_sm_budget() / B;   // persistent CTAs, 1 per SM (smem-bound): never more than one wave across the whole batch
-    if (gx < 1) gx = 1;
-    if (gx > ntiles) gx = ntiles;
-    dim3 grid(gx, B);
-    direction_head_tc_kernel<<<grid, 256, smem, stream>>>(feats, up_idx, up_w, wall, bc1, bf, vreg, creg, anchors, N, S, ce, anc_w);
+    int gx = etch_sm_budget();   // persistent CTAs, 1 per SM (smem-bound): never more than one wave
+    if (gx > ntiles * B) gx = ntiles * B;
+    direction_head_tc_kernel<<<gx, 256, smem, stream>>>(feats, up_idx, up_w, wall, bc1, bf, vreg, creg, anchors, B, N, S, ce, anc_w);
     so3_direction_kernel<<<etch_cdiv(B * N, 128), 128, 0, stream>>>(ce, B * N, dir);
     ETCH_RETURN_LAST();
 }

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
     const float4* __restrict__ krs,             // [60,24] {2/sigma * R_a k, |R_a k|^2/sigma}
     const float* __restrict__ Wc,               // [NPASS*16][12][2*COUT][4]  slabs: rows [W_hi; W_lo], canonical K-major tiles
     const float* __restrict__ bias,
-    int q, int P,
+    int B, int q, int P,
     float* __restrict__ zraw, double* __restrict__ stats)
 {
     using Cfg = V3Cfg<CIN, COUT, NN>;
@@ -122,8 +122,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
     __shared__ uint64_t f_full[RING], f_free[RING], g_full[GRING], a_full[2], a_free[2], w_full[2], w_free[2], acc_full, d_free;
     __shared__ uint32_t tmem_base;
 
-    const int b = blockIdx.y, tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
-    const int npts = blockIdx.x < P ? (P - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Scan-major schedule: every CTA takes its share of scan 0, then of scan 1, ... so that at any time the whole grid gathers
+    // from ONE scan's activations (19-38 MB: L2 resident) instead of all B of them (154 MB at B = 8: 3x the algorithmic DRAM
+    // traffic in the profile of the scan-parallel grid).
+    const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
+    const long long total_pts = (long long)B * P;      // global point gp = blockIdx.x + li * gridDim.x  ->  scan gp / P, point gp % P
+    const int npts = blockIdx.x < total_pts ? (int)((total_pts - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const uint32_t NIT = (uint32_t)npts * NPASS;
 
     for (int i = tid; i < NPAIRS; i += NTHREADS) s_krs[i] = __ldg(krs + i);
@@ -195,8 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                 const uint32_t fpt = next_f < total_chunks ? (next_f / NCHUNK) / NPASS : (uint32_t)npts;
                 if (next_g < (uint32_t)npts && next_g <= fpt + 2) {
                     const uint32_t gsl = next_g % GRING;
-                    const size_t p = (size_t)blockIdx.x + (size_t)next_g * gridDim.x;
-                    const size_t off = ((size_t)b * P + p) * NN;
+                    const size_t off = ((size_t)blockIdx.x + (size_t)next_g * gridDim.x) * NN;   // (b * P + p) * NN
                     const uint32_t bar = umma::smem_u32(&g_full[gsl]);
                     if (umma::elect_one()) {
                         umma::mbar_expect_tx(bar, NN * 20);
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                     const uint32_t bar = umma::smem_u32(&f_full[sl]);
                     const uint32_t dst = umma::smem_u32(s_f + sl * NB * NBR_SLOT);
                     int rows[NB];
+                    const int b = (int)(((size_t)blockIdx.x + (size_t)pt * gridDim.x) / (size_t)P);
 #pragma unroll
                     for (int jj = 0; jj < NB; ++jj) rows[jj] = (b * q + nb[jj]) * NA;
                     if (umma::elect_one()) {
@@ -317,13 +321,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d_free);
             bar_sync_named(2, 128);
-            const size_t p = (size_t)blockIdx.x + (size_t)pi * gridDim.x;
-            float4* dst = reinterpret_cast<float4*>(zraw + ((size_t)b * P + p) * NA * COUT);
+            const size_t gp = (size_t)blockIdx.x + (size_t)pi * gridDim.x, b = gp / (size_t)P;
+            float4* dst = reinterpret_cast<float4*>(zraw + gp * NA * COUT);
             for (int i = t; i < NA * COUT / 4; i += 128) dst[i] = reinterpret_cast<const float4*>(s_z)[i];
             if (t < COUT) {
                 float s = 0.f, ss = 0.f;
                 for (int r = 0; r < NA; ++r) { const float x = s_z[r * COUT + t]; s += x; ss = fmaf(x, x, ss); }
                 s_stat[2 * t] += (double)s; s_stat[2 * t + 1] += (double)ss;
+                if (pi + 1 == (uint32_t)npts || (gp + gridDim.x) / (size_t)P != b) {   // last point of this scan for this CTA: flush its statistics
+                    atomicAdd(stats + (b * COUT + t) * 2, s_stat[2 * t]);
+                    atomicAdd(stats + (b * COUT + t) * 2 + 1, s_stat[2 * t + 1]);
+                    s_stat[2 * t] = 0.0; s_stat[2 * t + 1] = 0.0;
+                }
             }
             bar_sync_named(2, 128);
         };
@@ -384,12 +393,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
             }
         }
         if (npts > 0 && wp < 4) epilogue((uint32_t)npts - 1);
-        if (wp < 4) {
-            if (t < COUT) {
-                atomicAdd(stats + ((size_t)b * COUT + t) * 2, s_stat[2 * t]);
-                atomicAdd(stats + ((size_t)b * COUT + t) * 2 + 1, s_stat[2 * t + 1]);
-            }
-        }
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -432,12 +435,11 @@ int launch_inter_v3(const float* xyz, const float* feat, const int* sample_idx, 
     }
     auto kern = inter_conv_v3_kernel<CIN, COUT, NN>;
     ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
-    int g = etch_sm_budget() / B;
-    if (g < 1) g = 1;
+    int g = etch_sm_budget();
     if (g > P) g = P;
-    dim3 grid((unsigned)g, (unsigned)B);
+    dim3 grid((unsigned)g);
     kern<<<grid, NTHREADS, Cfg::smem, stream>>>(tmap, reinterpret_cast<const float4*>(g4), nbr, reinterpret_cast<const float4*>(krs), Wc, bias,
-                                                q, P, zraw, stats);
+                                                B, q, P, zraw, stats);
     ETCH_RETURN_LAST();
 }
 
