@@ -44,13 +44,14 @@ struct AgemmCfg {
     static constexpr int LD = CIN + 4;
     static constexpr uint32_t A_BYTES = MROWS * CIN * 4;     // one (hi or lo) A tile
     static constexpr uint32_t B_BYTES = COUT * CIN * 4;      // one (hi or lo) weight slice
-    static constexpr int WR = (2 * B_BYTES <= 16384) ? 4 : 2; // weight ring depth
+    static constexpr int WR = (2 * B_BYTES <= 8192) ? 3 : 2;  // weight ring depth (3 keeps the c = 32 kernels at two CTAs per SM)
     static constexpr size_t smem = (size_t)4 * A_BYTES + (size_t)WR * 2 * B_BYTES + (size_t)NPAIR * LD * 4 + (size_t)2 * CIN * 4 +
                                    (size_t)((NA * J + 15) / 16) * 16 + 128;
+    static constexpr int CTAS_PER_SM = smem <= 112 * 1024 ? 2 : 1;   // latency-bound fill: a second CTA per SM hides it
 };
 
 template <int CIN, int COUT, int J, bool NORM_IN>
-__global__ void __launch_bounds__(288, 1) anchor_gemm_tc_kernel(
+__global__ void __launch_bounds__(288, (AgemmCfg<CIN, COUT, J>::CTAS_PER_SM)) anchor_gemm_tc_kernel(
     const float* __restrict__ xin,       // [B,Q,60,CIN]
     const int* __restrict__ src_idx,     // [B,P] or nullptr
     const int* __restrict__ tab,         // [60][J]
@@ -407,7 +408,10 @@ int launch_agemm_tc(const float* xin, const int* src_idx, const int* tab, const 
     static_assert(256 % COUT == 0, "statistics pass mapping");
     auto kern = anchor_gemm_tc_kernel<CIN, COUT, J, NORM>;
     ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
-    dim3 grid(grid_for_tc((P + TP - 1) / TP, B), B);
+    int gx = etch_sm_budget() * Cfg::CTAS_PER_SM / B;
+    if (gx < 1) gx = 1;
+    if (gx > (P + TP - 1) / TP) gx = (P + TP - 1) / TP;
+    dim3 grid(gx, B);
     kern<<<grid, 288, Cfg::smem, stream>>>(xin, src_idx, tab, Wc, bias, in_stats, in_count, Q, P, zraw, stats);
     ETCH_RETURN_LAST();
 }
