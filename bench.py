@@ -303,8 +303,15 @@ def run_etch(args, rank, world, local_rank):
     dom, (dom_calls, dom_ms) = next(((k, v) for k, v in top if _algo(k) is not None), top[0])
     scale = N / 5000.0
     algo = _algo(dom)
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp) and B == 8 and N == 5000:
+        ent = json.load(open(tp)).get("etch_" + dom)
+        if ent:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
     roofline = {"kernel": "etch_" + dom, "share_of_step": dom_ms / total_kernel_ms, "launches_per_step": dom_calls,
-                "avg_launch_ms": dom_ms / dom_calls, "traffic": None}
+                "avg_launch_ms": dom_ms / dom_calls, "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src}
     if algo is not None:
         flops = algo * 1e9 * scale * B  # all launches of this kernel in one step
         ach = flops / (dom_ms * 1e-3) / 1e12
@@ -355,7 +362,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--points", type=int, default=5000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=3, help="batches in flight (independent graph copies on their own streams)")
+    ap.add_argument("--in-flight", type=int, default=5, help="batches in flight (independent graph copies on their own streams)")
     ap.add_argument("--no-flush", action="store_true", help="skip the 256 MiB L2-flush write before every step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     args = ap.parse_args()
@@ -366,6 +373,10 @@ def main():
         run_reference(args, rank, world)
     else:
         run_etch(args, rank, world, local_rank)
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
     float4* s_g = reinterpret_cast<float4*>(s_z + 64 * COUT);              // [GRING][NN]
     int* s_nbr = reinterpret_cast<int*>(s_g + GRING * NN);                 // [GRING][NN]
     double* s_stat = reinterpret_cast<double*>(s_nbr + GRING * NN);        // [COUT][2]
-    __shared__ uint64_t f_full[RING], f_free[RING], g_full[GRING], a_full[2], a_free[2], w_full[2], w_free[2], acc_full, d_free;
+    __shared__ uint64_t f_full[RING], f_free[RING], g_full[GRING], a_full[2], a_free[2], w_full[2], w_free[2], acc_full, d_free, c_done;
     __shared__ uint32_t tmem_base;
 
     // Scan-major schedule: every CTA takes its share of scan 0, then of scan 1, ... so that at any time the whole grid gathers
@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
         }
         umma::mbar_init(&acc_full, 1);
         umma::mbar_init(&d_free, 4);
+        umma::mbar_init(&c_done, 15);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
         };
 
         if (NIT > 0) wgen(0);
+        bar_sync_named(1, CT);                       // weight tile of chunk 0 complete
         for (uint32_t it = 0; it <= NIT; ++it) {
             const bool work = it < NIT, parked = it >= 1;
             if (parked && wp < 4) {
@@ -352,15 +354,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
             }
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
-                if (work) {
-                    bar_sync_named(1, CT);
-                    if (gc + 1 < total_chunks) wgen(gc + 1);
-                }
+                // slab work first: it depends on nobody, so a warp that left the previous chunk early spends its skew here
                 if (parked && (c % SLAB_EVERY) == 0) {
 #pragma unroll
                     for (int sg = 0; sg < SLAB_GROUP; ++sg) slab_step((uint32_t)(c / SLAB_EVERY) * SLAB_GROUP + sg);
                 }
                 if (work) {
+                    // every warp has left chunk gc-1 (arrive/wait split instead of a CTA barrier): its weight tile may be
+                    // overwritten, and the tile of chunk gc, written before that, is complete
+                    if (gc >= 1) umma::mbar_wait(&c_done, (gc - 1) & 1);
+                    if (gc + 1 < total_chunks) wgen(gc + 1);
                     const uint32_t sl = gc % RING;
                     umma::mbar_wait(&f_full[sl], (gc / RING) & 1);
                     const unsigned char* fs = s_f + sl * NB * NBR_SLOT;
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                             for (int i = 0; i < 12; ++i) acc[cc][i] = fmaf(fv[cc], wv[i], acc[cc][i]);
                     }
                     __syncwarp();
-                    if (lane == 0) umma::mbar_arrive(&f_free[sl]);
+                    if (lane == 0) { umma::mbar_arrive(&f_free[sl]); umma::mbar_arrive(&c_done); }
                     ++gc;
                 }
             }
