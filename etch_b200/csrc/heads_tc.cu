@@ -276,6 +276,12 @@ __device__ __forceinline__ void dh_store_kv(uint32_t tmem, float* s_kv, int warp
     }
 }
 
+__device__ __forceinline__ float dh_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // softmax(q K^T) V for (token = my TMEM lane, my 4 heads); output written as (hi, lo) into the canonical O tile.
 // Online softmax over 3 chunks of 20 keys keeps the unrolled body small (the fully unrolled 4 x 60-key version
 // thrashed the instruction cache: stall_no_inst dominated the profile) at the cost of 3 extra exp's per head.
@@ -289,6 +295,8 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
         const int h = hq + hh;
         float qv[8];
         umma::tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + h * 8, qv);   // warp-collective: every lane takes part
+#pragma unroll
+        for (int d = 0; d < 8; ++d) qv[d] *= 1.4426950408889634f;         // scores in log2 units: every exponential is one MUFU.EX2
         float mx = -INFINITY, sum = 0.f;
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -307,14 +315,14 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
                 cm = fmaxf(cm, v);
             }
             const float mn = fmaxf(mx, cm);
-            const float sc = expf(mx - mn);   // first chunk: exp(-inf) = 0
+            const float sc = dh_ex2(mx - mn);   // first chunk: 2^(-inf) = 0
             mx = mn;
             sum *= sc;
 #pragma unroll
             for (int d = 0; d < 8; ++d) o[d] *= sc;
 #pragma unroll
             for (int j = 0; j < 20; ++j) {
-                const float p = expf(s[j] - mn);
+                const float p = dh_ex2(s[j] - mn);
                 sum += p;
                 const float* vr = s_kv + (base + j0 + j) * DH_LDKV + 64 + h * 8;
                 const float4 va = *reinterpret_cast<const float4*>(vr);
@@ -356,10 +364,13 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     float* s_part = s_kv + 2 * DH_NA * DH_LDKV;            // [2][128]
     float* s_w = s_part + 256;                             // [128]
     float* s_anc = s_w + 128;                              // [60][9]
+    __shared__ __align__(16) float s_bc1[64], s_bf[128], s_vreg[128];
     __shared__ uint64_t b_full[2], b_empty[2], bar_mma;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < DH_NA * 9; i += 256) s_anc[i] = __ldg(anchors + i);
+    if (tid < 64) s_bc1[tid] = __ldg(bc1 + tid);
+    if (tid < 128) { s_bf[tid] = __ldg(bf + tid); s_vreg[tid] = __ldg(vreg + tid); }
     if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
     if (tid == 0) {
         umma::mbar_init(&b_full[0], 1); umma::mbar_init(&b_full[1], 1);
@@ -451,8 +462,8 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
                     float4* pl_ = reinterpret_cast<float4*>(s_X + DH_XB + kc * (128 * 16) + row * 16);
                     const float4 xh = *ph, xl = *pl_;
                     const int n0 = half * 32 + i;
-                    const float nx = (xh.x + xl.x) + (v[i] + __ldg(bc1 + n0)), ny = (xh.y + xl.y) + (v[i + 1] + __ldg(bc1 + n0 + 1));
-                    const float nz = (xh.z + xl.z) + (v[i + 2] + __ldg(bc1 + n0 + 2)), nw = (xh.w + xl.w) + (v[i + 3] + __ldg(bc1 + n0 + 3));
+                    const float nx = (xh.x + xl.x) + (v[i] + s_bc1[n0]), ny = (xh.y + xl.y) + (v[i + 1] + s_bc1[n0 + 1]);
+                    const float nz = (xh.z + xl.z) + (v[i + 2] + s_bc1[n0 + 2]), nw = (xh.w + xl.w) + (v[i + 3] + s_bc1[n0 + 3]);
                     float4 hi, lo;
                     umma::split_tf32(nx, hi.x, lo.x); umma::split_tf32(ny, hi.y, lo.y);
                     umma::split_tf32(nz, hi.z, lo.z); umma::split_tf32(nw, hi.w, lo.w);
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int n0 = half * 64 + c0 + i;
-                    part = fmaf(fmaxf(v[i] + __ldg(bf + n0), 0.f), __ldg(vreg + n0), part);
+                    part = fmaf(fmaxf(v[i] + s_bf[n0], 0.f), s_vreg[n0], part);
                 }
             }
             s_part[half * 128 + row] = part;
