@@ -315,10 +315,14 @@ def run_etch(args, rank, world, local_rank):
     if algo is not None:
         flops = algo * 1e9 * scale * B  # all launches of this kernel in one step
         ach = flops / (dom_ms * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12   # FP32 SIMT peak at the measured SM clock
         roofline.update(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s", frac=ach / peaks["tensor"],
+                        fp32_simt_peak=fp32_peak, fp32_simt_frac=ach / fp32_peak,
                         peak_source="%s bf16 dense (MEASURED_PEAKS.json burst)" % peaks["which"],
-                        note="algorithmic fp32 flops (SURVEY 8d figure x scans) over the summed launch time of this kernel; the GEMM part "
-                             "runs as 3xTF32 on tcgen05 (3 MMAs per product, TF32 rate = half of bf16) to keep fp32-level parity")
+                        note="algorithmic fp32 flops (SURVEY 8d figure x scans) over the summed launch time of this kernel; its neighbour "
+                             "contraction (half of the flops) is not a dense GEMM and runs on the FP32 pipes (fp32_simt_frac is the same "
+                             "flops against the FP32 SIMT peak), the channel mixing runs as 3xTF32 on tcgen05 (3 MMAs per product, TF32 "
+                             "rate = half of bf16) to keep fp32-level parity")
     else:
         roofline.update(bound="latency", achieved=None, peak=None, unit=None, frac=None)
     kernels = {k: {"calls": c, "ms": round(t, 4)} for k, (c, t) in top}
