@@ -28,6 +28,10 @@ namespace {
 constexpr int NA = 60;
 constexpr int NK = 24;
 constexpr int NPAIRS = NA * NK;              // 1440 (anchor, kernel point) pairs
+#ifndef V3_JJ_UNROLL
+#define V3_JJ_UNROLL 1
+#endif
+constexpr int V3_JJ = V3_JJ_UNROLL;          // neighbours unrolled in the FMA phase
 #ifndef V3_SLEEP
 #define V3_SLEEP 256
 #endif
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                     umma::mbar_wait(&f_full[sl], (gc / RING) & 1);
                     const unsigned char* fs = s_f + sl * NB * NBR_SLOT;
                     const float* ws = s_w + (gc & 1) * (NB * NPAIRS) + w_off;
-#pragma unroll
+#pragma unroll(V3_JJ)            // 1, not NB: ptxas renames the 96 accumulators across an unrolled body and pays ~60 MOVs per chunk
                     for (int jj = 0; jj < NB; ++jj) {
                         const float4 fa = *reinterpret_cast<const float4*>(fs + jj * NBR_SLOT + offA);
                         const float4 fb = *reinterpret_cast<const float4*>(fs + jj * NBR_SLOT + offB);
