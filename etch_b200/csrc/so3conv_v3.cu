@@ -28,6 +28,9 @@ namespace {
 constexpr int NA = 60;
 constexpr int NK = 24;
 constexpr int NPAIRS = NA * NK;              // 1440 (anchor, kernel point) pairs
+#ifndef V3_FFMA2
+#define V3_FFMA2 0                           // 1: packed fma.rn.f32x2 accumulators (half the FMA issue slots; ptxas spills ~290 B/thread)
+#endif
 #ifndef V3_JJ_UNROLL
 #define V3_JJ_UNROLL 1
 #endif
@@ -78,6 +81,10 @@ struct V3Cfg {
 __device__ __forceinline__ void split_fast(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = x - hi;
+}
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
 }
 
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -255,7 +262,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
         const uint32_t tlane = (uint32_t)((wp & 3) * 32) << 16;
         const uint32_t park = tmem + tlane + PARK_COL + (uint32_t)(wp >> 2) * 96;
         const uint32_t a_st = (uint32_t)((3 * o) * A_LBO + a * 16);
+#if V3_FFMA2
+        unsigned long long acc[8][6];                    // T[a][8o + c][12h + 2j, 2j + 1] as packed fp32 pairs
+#else
         float acc[8][12];
+#endif
         uint32_t gc = 0, gs = 0;
         const uint32_t total_chunks = NIT * NCHUNK;
 
@@ -353,8 +364,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
             if (work) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
+#if V3_FFMA2
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) acc[c][i] = 0ull;
+#else
 #pragma unroll
                     for (int i = 0; i < 12; ++i) acc[c][i] = 0.f;
+#endif
             }
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
@@ -380,11 +396,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                         const float4 w1 = *reinterpret_cast<const float4*>(ws + jj * NPAIRS + 4);
                         const float4 w2 = *reinterpret_cast<const float4*>(ws + jj * NPAIRS + 8);
                         const float fv[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#if V3_FFMA2
+                        const unsigned long long ww[6] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y),
+                                                          pack2(w1.z, w1.w), pack2(w2.x, w2.y), pack2(w2.z, w2.w)};
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) {
+                            const unsigned long long ff = pack2(fv[cc], fv[cc]);
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[cc][i]) : "l"(ff), "l"(ww[i]));
+                        }
+#else
                         const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
                         for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
                             for (int i = 0; i < 12; ++i) acc[cc][i] = fmaf(fv[cc], wv[i], acc[cc][i]);
+#endif
                     }
                     __syncwarp();
                     if (lane == 0) { umma::mbar_arrive(&f_free[sl]); umma::mbar_arrive(&c_done); }
@@ -392,7 +419,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                 }
             }
             if (work) {
+#if V3_FFMA2
+                float av[96];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        av[cc * 12 + 2 * i] = __uint_as_float((uint32_t)acc[cc][i]);
+                        av[cc * 12 + 2 * i + 1] = __uint_as_float((uint32_t)(acc[cc][i] >> 32));
+                    }
+#else
                 const float* av = &acc[0][0];
+#endif
                 umma::tmem_st32(park, av);
                 umma::tmem_st32(park + 32, av + 32);
                 umma::tmem_st32(park + 64, av + 64);

@@ -98,3 +98,23 @@ def test_large_scans_through_the_whole_path(cuda, B, N):
     torch.cuda.synchronize()
     assert (out["labels"] == ref["labels"]).float().mean() > 0.999
     assert (out["vertices"] - ref["vertices"]).norm(dim=-1).mean().item() * 1000.0 < 0.05   # mm
+
+
+def test_mixed_size_stream_matches_per_scan_runs(cuda):
+    """BASELINE configs[4] (mixed stream): scans of three sizes, batched by size and run through the in-flight graph slots,
+    give each scan the result of running it alone."""
+    from etch_b200 import smpl_model, stream, synth
+    from etch_b200.runtime import ScanFitter
+    net, ms = _net(cuda)
+    args = types.SimpleNamespace(markerset=ms, smpl_model=smpl_model.synthetic_body(0), device="cuda:0")
+    sizes = [1024, 2048, 1024, 1531, 2048, 1024, 1024]
+    scans = {i: torch.from_numpy(synth.sample_scan(n, 100 + i)) for i, n in enumerate(sizes)}
+    plan = stream.plan_stream(sizes, 1, 2)
+    assert sum(len(ids) for _, ids in plan[0]) == len(sizes)
+    fitter = ScanFitter(net, args, use_graph=True, in_flight=2)
+    got = stream.run_stream(fitter, scans, plan[0], cuda, pad_to=2)
+    eager = ScanFitter(net, args, use_graph=False)
+    for i in (0, 3, 4, 6):
+        ref = eager(scans[i][None].to(cuda))
+        assert (got[i]["labels"] == ref["labels"][0]).float().mean() > 0.999
+        assert (got[i]["vertices"] - ref["vertices"][0]).norm(dim=-1).mean().item() * 1000.0 < 0.05   # mm

@@ -1,0 +1,66 @@
+"""Throughput of a mixed-size scan stream (BASELINE.json configs[4]) through etch_b200.stream on the GPUs of one box.
+
+    python tools/bench_mixed.py [--scans 48] [--batch 8] [--passes 3]            (1 GPU)
+    python -m torch.distributed.run --nproc-per-node N tools/bench_mixed.py ...  (N GPUs: the stream is dealt longest-first)
+
+Prints one JSON line (rank 0): scans/s over all ranks, per-size counts, the plan's load imbalance.  Synthetic scans of 5k / 10k /
+20k points (2:1:1), seeded weights; device-resident inputs; time = max over ranks of the CUDA-event time of the timed passes.
+"""
+import argparse
+import json
+import os
+import sys
+import types
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from etch_b200 import sharding, stream, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scans", type=int, default=48)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--passes", type=int, default=3)
+    ap.add_argument("--in-flight", type=int, default=3)
+    a = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sizes = [(5000, 5000, 10000, 20000)[i % 4] for i in range(a.scans * world)]
+    plan = stream.plan_stream(sizes, world, a.batch)
+    mine = plan[rank]
+    scans = {i: torch.from_numpy(synth.sample_scan(sizes[i], 500 + i)).to(dev) for _, ids in mine for i in ids}
+    pipe = bench.Pipeline(dev, use_graph=True, in_flight=a.in_flight)
+    stream.run_stream(pipe.fitter, scans, mine, dev, pad_to=a.batch)     # warm-up: captures one graph set per point count
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.passes):
+        out = stream.run_stream(pipe.fitter, scans, mine, dev, pad_to=a.batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    sharding.max_over_ranks(ms)
+    assert all(torch.isfinite(v["vertices"]).all() for v in out.values())
+    if rank == 0:
+        loads = [sum(stream.batch_cost(len(ids), n) for n, ids in rb) for rb in plan]
+        print(json.dumps({"metric": "scans/sec (net fwd + SMPL fit), mixed stream", "value": len(sizes) * a.passes / (ms.item() * 1e-3),
+                          "unit": "scans/s", "n_gpus": world, "passes": a.passes, "ms_per_pass": ms.item() / a.passes,
+                          "config": {"workload": "mixed stream 5k/5k/10k/20k points (BASELINE configs[4]), batches of <= %d equal-size scans, "
+                                                 "longest-first over %d rank(s)" % (a.batch, world),
+                                     "scans": len(sizes), "in_flight": a.in_flight,
+                                     "plan_load_imbalance": (max(loads) - min(loads)) / max(loads) if max(loads) > 0 else 0.0}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
