@@ -18,6 +18,7 @@
 //  * kNN: one thread per query running the reference's max-heap verbatim (so equal-distance order is identical),
 //    supports staged through shared memory tiles.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -143,6 +144,144 @@ __global__ void __launch_bounds__(1024, 1) fps_packed_kernel(const float* __rest
     s.xyz = xyz; s.n = end_n - start_n; s.m = end_m - start_m; s.base = start_n;
     s.out = idx + start_m;
     fps_segment<PPT, true, SMEM_XY>(s, T_ref, fps_smem, fps_smem + s.n, slots);
+}
+
+// ------------------------------------------------------------------------------------------------ cluster FPS (large clouds)
+// FPS is a chain of m-1 dependent steps, each a distance update of every point + an argmax.  One CTA keeps up to ~8k points
+// in registers; beyond that (BASELINE configs[2..4]: 10k / 20k-point scans) the register file of one SM is too small and the
+// per-step work (n x ~20 instructions) too long for one SM.  Here a thread-block CLUSTER of CL = 4 or 8 CTAs owns one scan: each
+// CTA holds n / CL points in registers, finds its local winner exactly as fps_segment does, posts (value, tie key, xyz)
+// into every peer's shared memory (distributed shared memory) and one cluster barrier later every CTA picks the same global
+// winner from the CL candidates -- no global-memory round trip on the critical path.  Same (value, tie key) order as the
+// single-CTA kernel, hence the same indices as the reference.
+constexpr int FPS_CL_MAX = 8;               // portable cluster size limit
+constexpr int FPS_CLUSTER_MIN = 8192;      // clouds above this size use the cluster kernel
+struct __align__(16) FpsCand { unsigned v, t; float x, y, z; unsigned pad[3]; };
+
+template <int PPT, bool PACKED, int FPS_CL>
+__global__ void __launch_bounds__(1024, 1)
+fps_cluster_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, const int* __restrict__ new_offset, int n_bcn,
+                   int m_bcn, int T_ref, int* __restrict__ idx) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float fps_smem[];            // [3][per] coordinates of this CTA's points (winner look-up)
+    __shared__ uint2 slots[2][32];
+    __shared__ FpsCand cand[2][FPS_CL];
+    const int rank = (int)cluster.block_rank();
+    const int scan = blockIdx.x / FPS_CL;
+    FpsSeg s;
+    if (PACKED) {
+        const int start_n = scan == 0 ? 0 : offset[scan - 1], end_n = offset[scan];
+        const int start_m = scan == 0 ? 0 : new_offset[scan - 1], end_m = new_offset[scan];
+        s.xyz = xyz; s.n = end_n - start_n; s.m = end_m - start_m; s.base = start_n; s.out = idx + start_m;
+    } else {
+        s.xyz = xyz + (size_t)scan * 3 * n_bcn; s.n = n_bcn; s.m = m_bcn; s.base = 0; s.out = idx + (size_t)scan * m_bcn;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (s.n + FPS_CL - 1) / FPS_CL, kbase = rank * per;
+    float* sx = fps_smem; float* sy = sx + per; float* sz = sy + per;
+    const int Tm1 = T_ref - 1;
+    int lg = 0;
+    while ((1 << lg) < T_ref) ++lg;
+    const int shift = 32 - lg;
+
+    float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+    unsigned valid = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const int jl = tid + i * 1024, k = kbase + jl;
+        float x = 0.f, y = 0.f, z = 0.f;
+        bool ok = jl < per && k < s.n;
+        if (ok) {
+            fps_load<PACKED>(s, k, x, y, z);
+            sx[jl] = x; sy[jl] = y; sz[jl] = z;
+            if (!PACKED) {
+                const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+                if ((double)mag <= 1e-3) ok = false;
+            }
+        }
+        px[i] = x; py[i] = y; pz[i] = z; tmp[i] = 1e10f;
+        if (ok) valid |= 1u << i;
+    }
+    if (rank == 0 && tid == 0 && s.m > 0) s.out[0] = s.base;
+    for (int i = tid; i < 64; i += 1024) slots[i >> 5][i & 31] = make_uint2(0u, 0u);
+    float x1, y1, z1;
+    fps_load<PACKED>(s, 0, x1, y1, z1);
+    __syncthreads();
+    cluster.sync();                                // every CTA's shared memory is live before the first remote store
+
+    for (int j = 1; j < s.m; ++j) {
+        unsigned bv = 0u, bt = 0u;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            if (valid & (1u << i)) {
+                const int k = kbase + tid + i * 1024;
+                const float d = etch_sqdist3(px[i] - x1, py[i] - y1, pz[i] - z1);
+                const float d2 = fminf(d, tmp[i]);
+                tmp[i] = d2;
+                const unsigned vb = __float_as_uint(d2);
+                const unsigned tk = fps_tie_key(k, Tm1, shift);
+                if (vb > bv || (vb == bv && tk > bt)) { bv = vb; bt = tk; }
+            }
+        }
+        const unsigned wv = __reduce_max_sync(0xffffffffu, bv);
+        const unsigned wt = __reduce_max_sync(0xffffffffu, bv == wv ? bt : 0u);
+        const int buf = j & 1;
+        if (lane == 0) slots[buf][warp] = make_uint2(wv, wt);
+        __syncthreads();
+        if (warp == 0) {
+            const uint2 sl = slots[buf][lane];
+            const unsigned gv = __reduce_max_sync(0xffffffffu, sl.x);
+            const unsigned gt = __reduce_max_sync(0xffffffffu, sl.x == gv ? sl.y : 0u);
+            if (lane < FPS_CL) {                   // post this CTA's candidate into peer `lane`
+                FpsCand c;
+                c.v = gv; c.t = gt; c.x = 0.f; c.y = 0.f; c.z = 0.f; c.pad[0] = c.pad[1] = c.pad[2] = 0u;
+                if (gt) {
+                    const int kl = (int)(0x1FFFFFu - (gt & 0x1FFFFFu)) - kbase;
+                    c.x = sx[kl]; c.y = sy[kl]; c.z = sz[kl];
+                }
+                FpsCand* dst = cluster.map_shared_rank(&cand[buf][rank], lane);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(c.v, c.t, __float_as_uint(c.x), __float_as_uint(c.y));
+                reinterpret_cast<float*>(dst)[4] = c.z;
+            }
+        }
+        cluster.sync();
+        unsigned gv = 0u, gt = 0u;
+        int win = 0;
+#pragma unroll
+        for (int r = 0; r < FPS_CL; ++r) {
+            const unsigned v = cand[buf][r].v, t = cand[buf][r].t;
+            if (v > gv || (v == gv && t > gt)) { gv = v; gt = t; win = r; }
+        }
+        int old = 0;
+        if (gt) {
+            old = (int)(0x1FFFFFu - (gt & 0x1FFFFFu));
+            x1 = cand[buf][win].x; y1 = cand[buf][win].y; z1 = cand[buf][win].z;
+        } else {
+            fps_load<PACKED>(s, 0, x1, y1, z1);    // no candidate at all: the reference keeps besti = 0
+        }
+        if (rank == 0 && tid == 0) s.out[j] = s.base + old;
+    }
+    cluster.sync();                                // nobody exits while a peer may still write into its shared memory
+}
+
+
+// launch a cluster kernel (cluster size is a launch attribute so that one template serves 4- and 8-CTA clusters)
+template <typename Kern, typename... Args>
+static int fps_cluster_launch(Kern kern, int clusters, int cl, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * cl));
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (smem > 48 * 1024) ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ETCH_TRY(cudaLaunchKernelEx(&cfg, kern, args...));
+    return ETCH_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ ball query
@@ -414,6 +553,17 @@ ETCH_API int etch_fps_bcn(const float* xyz, int B, int n, int m, int* idx, cudaS
     if (!xyz || !idx || B <= 0 || n <= 0 || m < 0 || n > 28672) return ETCH_EINVAL;
     if (m == 0) return ETCH_OK;
     const int T = etch_opt_n_threads(n);
+    if (n > FPS_CLUSTER_MIN) {   // large clouds: a cluster of 4 (n <= 16k) or 8 CTAs per scan, <= 4 points per thread
+        const int cl = n <= 16384 ? 4 : 8;
+        const int per = (n + cl - 1) / cl, cppt = (per + 1023) / 1024;
+        const size_t sm = (size_t)per * 12;
+        const int* np_ = nullptr;
+#define LC(P)                                                                                                              \
+    return cl == 4 ? fps_cluster_launch(fps_cluster_kernel<P, false, 4>, B, 4, sm, stream, xyz, np_, np_, n, m, T, idx)    \
+                   : fps_cluster_launch(fps_cluster_kernel<P, false, 8>, B, 8, sm, stream, xyz, np_, np_, n, m, T, idx);
+        if (cppt <= 1) { LC(1) } else if (cppt <= 2) { LC(2) } else if (cppt <= 3) { LC(3) } else { LC(4) }
+#undef LC
+    }
     const int nt = n >= 1024 ? 1024 : ((n + 31) / 32) * 32;
     const int ppt = (n + nt - 1) / nt;
 #define L(P, SX)                                                                                               \
@@ -438,6 +588,16 @@ ETCH_API int etch_fps_packed(int b, int n_max, const float* xyz, const int* offs
     (void)tmp;
     if (!xyz || !offset || !new_offset || !idx || b <= 0 || n_max <= 0 || n_max > 28672) return ETCH_EINVAL;
     const int T = etch_opt_n_threads(n_max);
+    if (n_max > FPS_CLUSTER_MIN) {
+        const int cl = n_max <= 16384 ? 4 : 8;
+        const int per = (n_max + cl - 1) / cl, cppt = (per + 1023) / 1024;
+        const size_t sm = (size_t)per * 12;
+#define LC(P)                                                                                                                      \
+    return cl == 4 ? fps_cluster_launch(fps_cluster_kernel<P, true, 4>, b, 4, sm, stream, xyz, offset, new_offset, 0, 0, T, idx)    \
+                   : fps_cluster_launch(fps_cluster_kernel<P, true, 8>, b, 8, sm, stream, xyz, offset, new_offset, 0, 0, T, idx);
+        if (cppt <= 1) { LC(1) } else if (cppt <= 2) { LC(2) } else if (cppt <= 3) { LC(3) } else { LC(4) }
+#undef LC
+    }
     const int nt = n_max >= 1024 ? 1024 : ((n_max + 31) / 32) * 32;
     const int ppt = (n_max + nt - 1) / nt;
 #define L(P, SX)                                                                                               \

@@ -31,7 +31,7 @@ def _tie_cloud(B, n, seed):
     return np.ascontiguousarray(g.transpose(0, 2, 1))
 
 
-@pytest.mark.parametrize("B,n", [(1, 5000), (8, 5000), (2, 10000), (2, 20000), (3, 777), (2, 64), (1, 1500)])
+@pytest.mark.parametrize("B,n", [(1, 5000), (8, 5000), (2, 10000), (2, 20000), (3, 777), (2, 64), (1, 1500), (2, 8192), (3, 8193), (1, 28672)])
 def test_fps_bcn_matches_oracle(cuda, B, n):
     g, _, _ = _ext()
     x = _scan_bcn(B, n, 11)
@@ -126,7 +126,7 @@ def test_knn_cross_levels_and_short_segments(cuda):
 
 
 @pytest.mark.parametrize("segs,ties", [([5000] * 4, False), ([1250, 1250], False), ([312, 312, 312], True), ([78, 40, 19, 300], True),
-                                        ([20000, 20000], False)])
+                                        ([20000, 20000], False), ([10000, 333, 20000], False), ([9000, 12000], True)])
 def test_fps_packed_matches_oracle(cuda, segs, ties):
     _, _, p = _ext()
     rng = np.random.default_rng(9)
