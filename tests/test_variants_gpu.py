@@ -118,3 +118,33 @@ def test_mixed_size_stream_matches_per_scan_runs(cuda):
         ref = eager(scans[i][None].to(cuda))
         assert (got[i]["labels"] == ref["labels"][0]).float().mean() > 0.999
         assert (got[i]["vertices"] - ref["vertices"][0]).norm(dim=-1).mean().item() * 1000.0 < 0.05   # mm
+
+
+@pytest.mark.parametrize("c,ns,n", [(64, 8, 1000), (128, 8, 517), (128, 16, 2048), (256, 16, 333), (512, 16, 19), (256, 8, 130)])
+def test_pt_attention_tc_unit(cuda, c, ns, n):
+    """etch_pt_attention_tc against etch_pt_attention on random operands: every channel width of the two PointTransformers,
+    both neighbour counts, row counts that are not a multiple of the 128-row tile (ragged last tile, a single partial tile)."""
+    from etch_b200 import _lib as L
+    from etch_b200.models import tc
+    g = torch.Generator().manual_seed(c * 1000 + ns + n)
+    T = c // 8
+    f = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).to(cuda).contiguous()  # noqa: E731
+    p, qkv = f(n, 3, scale=0.3), f(n, 3 * c)
+    idx = torch.randint(0, n, (n, ns), generator=g, dtype=torch.int32).to(cuda)
+    P0, p0b, P3, p3b = f(3, 3), f(3, scale=0.1), f(c, 3), f(c, scale=0.1)
+    s0, h0, so, ho = 1 + f(c, scale=0.1), f(c, scale=0.1), 1 + f(c, scale=0.1), f(c, scale=0.1)
+    W1, b1, W2, b2 = f(T, c, scale=c ** -0.5), f(T, scale=0.1), f(T, T, scale=T ** -0.5), f(T, scale=0.1)
+    ref = torch.empty(n, c, device=cuda)
+    L.call("pt_attention", L.ptr(p), L.ptr(qkv), L.ptr(idx), L.ptr(P0), L.ptr(p0b), L.ptr(P3), L.ptr(p3b), L.ptr(s0), L.ptr(h0),
+           L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(so), L.ptr(ho), n, ns, c, L.ptr(ref))
+    chan = torch.cat([P3, p3b[:, None], s0[:, None], h0[:, None], so[:, None], ho[:, None]], 1).contiguous()
+    tp = max(T, 16)
+    wa = torch.zeros(tp, c)
+    wa[:T] = W1.cpu()
+    W1c = torch.stack([tc.tc_operand(wa[:, k:k + 64].contiguous(), "cpu") for k in range(0, c, 64)], 0).contiguous().to(cuda)
+    out = torch.empty(n, c, device=cuda)
+    L.call("pt_attention_tc", L.ptr(p), L.ptr(qkv), L.ptr(idx), L.ptr(P0), L.ptr(p0b), L.ptr(chan), L.ptr(W1c), L.ptr(b1), L.ptr(W2),
+           L.ptr(b2), n, ns, c, L.ptr(out))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 1e-4
