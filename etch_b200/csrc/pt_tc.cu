@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict
             for (int j = 0; j < NS; ++j) { lg[j] = col[j * LDL]; mx = fmaxf(mx, lg[j]); }
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < NS; ++j) { lg[j] = expf(lg[j] - mx); s += lg[j]; }
+            for (int j = 0; j < NS; ++j) { lg[j] = exp2f((lg[j] - mx) * 1.4426950408889634f); s += lg[j]; }
             const float inv = 1.0f / s;
 #pragma unroll
             for (int j = 0; j < NS; ++j) col[j * LDL] = lg[j] * inv;

@@ -197,11 +197,12 @@ __device__ __forceinline__ void bulk_load_region(void* dst_smem, const void* src
     }
 }
 
-// fp32 -> (hi, lo) with hi = round-to-nearest tf32, lo = x - hi (exact); the tensor core truncates lo to tf32
+// fp32 -> (hi, lo) with hi = x rounded to TF32 (nearest, ties away from zero) and lo = x - hi (exact); the tensor core
+// truncates lo to tf32.  Integer form of cvt.rna.tf32.f32 -- same result for every finite input below 2^128 * (1 - 2^-11),
+// 2 instructions instead of the 5 the cvt expands to (it adds NaN/Inf handling); etch_b200/models/tc.py uses the same formula
+// for the weight operands.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
     lo = x - hi;
 }
 
