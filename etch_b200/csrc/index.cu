@@ -535,6 +535,194 @@ __global__ void __launch_bounds__(KNNW_WARPS * 32) knn_warp_kernel(int m, const 
     }
 }
 
+// ---- grid-accelerated kNN (same results as the brute-force scan) ----
+// The reference tests every query against every point of its segment (m x n distance tests, quadratic in the scan size).
+// Here the candidates of each segment are binned into a uniform grid (cell size ~ the expected nsample-neighbour radius of a
+// surface sampling), a query walks the cells around it shell by shell and stops when its nsample-th distance is strictly
+// smaller than the distance to everything unexplored.  Without equal distances that set, sorted ascending, IS the reference's
+// heap-sorted output; any tie inside the result or at its boundary (or a segment shorter than nsample) sends the query to
+// knn_serial_exact, the literal emulation, so indices and distances stay bit-exact.
+constexpr int KG_MAXCELLS = 65536;   // per segment
+constexpr int KG_MAXDIM = 64;
+
+struct __align__(16) KnnGrid { float ox, oy, oz, inv_h; int nx, ny, nz, ncell; float h; int pad0, pad1, pad2; };
+
+__global__ void __launch_bounds__(256) knn_grid_setup_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, int nsample,
+                                                             KnnGrid* __restrict__ grids) {
+    const int b = blockIdx.x;
+    const int start = b == 0 ? 0 : __ldg(offset + b - 1), end = __ldg(offset + b);
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = start + threadIdx.x; i < end; i += 256)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = __ldg(xyz + (size_t)i * 3 + a); lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    __shared__ float s_lo[3][8], s_hi[3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+        if ((threadIdx.x & 31) == 0) { s_lo[a][threadIdx.x >> 5] = lo[a]; s_hi[a][threadIdx.x >> 5] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        KnnGrid g;
+        float e[3];
+        float o3[3];
+        for (int a = 0; a < 3; ++a) {
+            float l = s_lo[a][0], h = s_hi[a][0];
+            for (int w = 1; w < 8; ++w) { l = fminf(l, s_lo[a][w]); h = fmaxf(h, s_hi[a][w]); }
+            if (end <= start) { l = 0.f; h = 0.f; }
+            o3[a] = l;
+            e[a] = fmaxf(h - l, 1e-6f);
+        }
+        const int n = max(end - start, 1);
+        // expected nsample-neighbour radius of a surface sampling: half of the bounding-box surface as the area estimate
+        const float area = e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+        float h = 1.1f * sqrtf((float)nsample * area / (3.14159265f * (float)n));
+        h = fmaxf(h, fmaxf(e[0], fmaxf(e[1], e[2])) / (float)KG_MAXDIM);
+        int nx, ny, nz;
+        for (;;) {
+            nx = min(KG_MAXDIM, (int)(e[0] / h) + 1); ny = min(KG_MAXDIM, (int)(e[1] / h) + 1); nz = min(KG_MAXDIM, (int)(e[2] / h) + 1);
+            if ((long long)nx * ny * nz <= KG_MAXCELLS) break;
+            h *= 1.26f;
+        }
+        g.ox = o3[0]; g.oy = o3[1]; g.oz = o3[2]; g.inv_h = 1.0f / h; g.h = h;
+        g.nx = nx; g.ny = ny; g.nz = nz; g.ncell = nx * ny * nz; g.pad0 = g.pad1 = g.pad2 = 0;
+        grids[b] = g;
+    }
+}
+
+__device__ __forceinline__ int kg_cell_coord(float v, float o, float inv_h, int n) {
+    const int c = (int)floorf((v - o) * inv_h);
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+__device__ __forceinline__ int kg_segment(int i, const int* __restrict__ offset, int nbatch) {
+    int b = 0;
+    while (b < nbatch - 1 && !(i < __ldg(offset + b))) ++b;
+    return b;
+}
+
+// MODE 0: histogram; MODE 1: scatter (x, y, z, index) into cell order
+template <int MODE>
+__global__ void __launch_bounds__(256) knn_grid_bin_kernel(const float* __restrict__ xyz, const int* __restrict__ offset, int nbatch, int n,
+                                                           const KnnGrid* __restrict__ grids, int* __restrict__ cells, float4* __restrict__ sorted) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int b = kg_segment(i, offset, nbatch);
+    const KnnGrid g = grids[b];
+    const float x = __ldg(xyz + (size_t)i * 3), y = __ldg(xyz + (size_t)i * 3 + 1), z = __ldg(xyz + (size_t)i * 3 + 2);
+    const int c = (kg_cell_coord(z, g.oz, g.inv_h, g.nz) * g.ny + kg_cell_coord(y, g.oy, g.inv_h, g.ny)) * g.nx + kg_cell_coord(x, g.ox, g.inv_h, g.nx);
+    int* cell = cells + (size_t)b * (KG_MAXCELLS + 1) + c;
+    if (MODE == 0) atomicAdd(cell, 1);
+    else sorted[atomicAdd(cell, 1)] = make_float4(x, y, z, __int_as_float(i));
+}
+
+// exclusive scan of the per-cell counts of one segment -> first slot of every cell (global slot = segment start + prefix);
+// `starts` keeps the result, `cursor` is a working copy for the scatter pass
+__global__ void __launch_bounds__(1024) knn_grid_scan_kernel(const int* __restrict__ offset, const KnnGrid* __restrict__ grids,
+                                                             int* __restrict__ starts, int* __restrict__ cursor) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int base = b == 0 ? 0 : __ldg(offset + b - 1);
+    const int ncell = grids[b].ncell;
+    int* st = starts + (size_t)b * (KG_MAXCELLS + 1);
+    int* cu = cursor + (size_t)b * (KG_MAXCELLS + 1);
+    const int per = (ncell + 1023) / 1024;
+    const int c0 = tid * per, c1 = min(ncell, c0 + per);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += st[c];
+    __shared__ int s_part[1024];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = base + s_part[tid] - sum;
+    for (int c = c0; c < c1; ++c) { const int cnt = st[c]; st[c] = run; cu[c] = run; run += cnt; }
+    if (tid == 1023) st[ncell] = base + s_part[1023];
+}
+
+template <int NS>
+__global__ void __launch_bounds__(128) knn_grid_query_kernel(int m, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+                                                             const int* __restrict__ offset, const int* __restrict__ new_offset, int nbatch,
+                                                             const KnnGrid* __restrict__ grids, const int* __restrict__ starts,
+                                                             const float4* __restrict__ sorted, int* __restrict__ idx, float* __restrict__ dist2) {
+    const int pt = blockIdx.x * 128 + threadIdx.x;
+    if (pt >= m) return;
+    const int b = kg_segment(pt, new_offset, nbatch);
+    const int start = b == 0 ? 0 : __ldg(offset + b - 1), end = __ldg(offset + b);
+    const float qx = __ldg(new_xyz + (size_t)pt * 3), qy = __ldg(new_xyz + (size_t)pt * 3 + 1), qz = __ldg(new_xyz + (size_t)pt * 3 + 2);
+    int* oi = idx + (size_t)pt * NS;
+    float* od = dist2 + (size_t)pt * NS;
+    if (end - start < NS) { knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, oi, od); return; }
+    const KnnGrid g = grids[b];
+    const int* st = starts + (size_t)b * (KG_MAXCELLS + 1);
+    const int cx = kg_cell_coord(qx, g.ox, g.inv_h, g.nx), cy = kg_cell_coord(qy, g.oy, g.inv_h, g.ny), cz = kg_cell_coord(qz, g.oz, g.inv_h, g.nz);
+    float ld[NS];
+    int li[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { ld[i] = 3e38f; li[i] = start; }
+    float rej = 3e38f;      // smallest distance that is NOT in the list
+    int cnt = 0;
+    const int rmax = max(g.nx, max(g.ny, g.nz));
+    for (int r = 0; r <= rmax; ++r) {
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1), y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) {
+                const bool face = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+                // cells of this (z, y) row that belong to shell r: the whole row on a face, else only the two x ends
+                for (int xr = 0; xr < 2; ++xr) {
+                    int xa, xb;
+                    if (face) { if (xr == 1) break; xa = x0; xb = x1; }
+                    else {
+                        const int xe = xr == 0 ? cx - r : cx + r;
+                        if (xe < 0 || xe >= g.nx || (xr == 1 && r == 0)) continue;
+                        xa = xb = xe;
+                    }
+                    const int crow = (z * g.ny + y) * g.nx;
+                    const int s0 = __ldg(st + crow + xa), s1 = __ldg(st + crow + xb + 1);   // consecutive cells are consecutive slots
+                    for (int s = s0; s < s1; ++s) {
+                        const float4 c = __ldg(sorted + s);
+                        const float d = etch_sqdist3(qx - c.x, qy - c.y, qz - c.z);
+                        ++cnt;
+                        if (d < ld[NS - 1] || (d == ld[NS - 1] && false)) {
+                            rej = fminf(rej, ld[NS - 1]);
+                            float cd = d;
+                            int ci = __float_as_int(c.w);
+#pragma unroll
+                            for (int i = 0; i < NS; ++i) {          // sorted insertion by swapping through the list
+                                if (cd < ld[i]) { const float td = ld[i]; const int ti = li[i]; ld[i] = cd; li[i] = ci; cd = td; ci = ti; }
+                            }
+                        } else {
+                            rej = fminf(rej, d);
+                        }
+                    }
+                }
+            }
+        if (cnt >= NS) {
+            // distance from the query to everything outside the explored cube (faces beyond the grid have nothing behind them)
+            float dout = 3e38f;
+            if (cx - r > 0) dout = fminf(dout, qx - (g.ox + (float)(cx - r) * g.h));
+            if (cx + r + 1 < g.nx) dout = fminf(dout, g.ox + (float)(cx + r + 1) * g.h - qx);
+            if (cy - r > 0) dout = fminf(dout, qy - (g.oy + (float)(cy - r) * g.h));
+            if (cy + r + 1 < g.ny) dout = fminf(dout, g.oy + (float)(cy + r + 1) * g.h - qy);
+            if (cz - r > 0) dout = fminf(dout, qz - (g.oz + (float)(cz - r) * g.h));
+            if (cz + r + 1 < g.nz) dout = fminf(dout, g.oz + (float)(cz + r + 1) * g.h - qz);
+            if (dout >= 3e38f) break;                                  // the cube covers the whole grid
+            dout -= 1e-3f * g.h;                                       // margin for the rounding of the cell assignment
+            if (dout > 0.f && ld[NS - 1] < dout * dout) break;
+        }
+    }
+    bool tie = rej <= ld[NS - 1];
+#pragma unroll
+    for (int i = 1; i < NS; ++i) tie |= ld[i] == ld[i - 1];
+    if (tie || cnt < NS) { knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, oi, od); return; }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { oi[i] = li[i]; od[i] = ld[i]; }
+}
+
 }  // namespace
 
 static int g_sm_budget = 148;
@@ -644,6 +832,32 @@ ETCH_API int etch_knn_packed(int m, int nsample, const float* xyz, const float* 
     else if (nsample == 8) knn_warp_kernel<8><<<wgrid, KNNW_WARPS * 32, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
     else if (nsample == 16) knn_warp_kernel<16><<<wgrid, KNNW_WARPS * 32, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
     else knn_packed_kernel<0><<<grid, 64, 0, stream>>>(m, nsample, xyz, new_xyz, offset, new_offset, nbatch, idx, dist2);
+    ETCH_RETURN_LAST();
+}
+
+// Grid-accelerated kNN with the results of etch_knn_packed (bit-exact, see knn_grid_query_kernel); nsample in {3, 8, 16}.
+// n = rows of xyz.  scratch: caller-owned, etch_knn_grid_scratch_bytes(n, nbatch) bytes, 16-byte aligned.
+ETCH_API long long etch_knn_grid_scratch_bytes(int n, int nbatch) {
+    return (long long)nbatch * 64 + 2ll * nbatch * (KG_MAXCELLS + 1) * 4 + 16 + (long long)n * 16;
+}
+ETCH_API int etch_knn_grid(int m, int nsample, const float* xyz, int n, const float* new_xyz, const int* offset, const int* new_offset,
+                           int nbatch, int* idx, float* dist2, void* scratch, cudaStream_t stream) {
+    if (!xyz || !new_xyz || !offset || !new_offset || !idx || !dist2 || !scratch || m <= 0 || n <= 0 || nbatch <= 0) return ETCH_EINVAL;
+    if (nsample != 3 && nsample != 8 && nsample != 16) return ETCH_EINVAL;
+    unsigned char* sp = static_cast<unsigned char*>(scratch);
+    KnnGrid* grids = reinterpret_cast<KnnGrid*>(sp);
+    int* starts = reinterpret_cast<int*>(sp + (size_t)nbatch * 64);
+    int* cursor = starts + (size_t)nbatch * (KG_MAXCELLS + 1);
+    float4* sorted = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(cursor + (size_t)nbatch * (KG_MAXCELLS + 1)) + 15) & ~(uintptr_t)15);
+    ETCH_TRY(cudaMemsetAsync(starts, 0, (size_t)nbatch * (KG_MAXCELLS + 1) * 4, stream));
+    knn_grid_setup_kernel<<<nbatch, 256, 0, stream>>>(xyz, offset, nsample, grids);
+    knn_grid_bin_kernel<0><<<etch_cdiv(n, 256), 256, 0, stream>>>(xyz, offset, nbatch, n, grids, starts, sorted);
+    knn_grid_scan_kernel<<<nbatch, 1024, 0, stream>>>(offset, grids, starts, cursor);
+    knn_grid_bin_kernel<1><<<etch_cdiv(n, 256), 256, 0, stream>>>(xyz, offset, nbatch, n, grids, cursor, sorted);
+    const int grid = etch_cdiv(m, 128);
+    if (nsample == 3) knn_grid_query_kernel<3><<<grid, 128, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
+    else if (nsample == 8) knn_grid_query_kernel<8><<<grid, 128, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
+    else knn_grid_query_kernel<16><<<grid, 128, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
     ETCH_RETURN_LAST();
 }
 

@@ -5,6 +5,7 @@ functions only allocate buffers and launch kernels through the C ABI.
 Reference modules restated: src/models/direction_backbones.py:129-223, src/models/pointtransformer_seg.py (all),
 src/models/models_pointcloud.py:94-126.
 """
+import ctypes
 import math
 import os
 
@@ -16,6 +17,7 @@ from .spec import PT_BLOCKS, PT_NSAMPLE, PT_STRIDE
 
 EPS_BN = 1e-5
 USE_TC = os.environ.get("ETCH_B200_NO_TC", "0") != "1"  # tcgen05 kernels (default) vs fp32 CUDA-core versions
+KNN_GRID = os.environ.get("ETCH_B200_KNN", "grid") == "grid"   # kNN through a uniform grid (default) or the brute-force scan
 PT_ATTN_TC = os.environ.get("ETCH_B200_PT_ATTN", "tc") == "tc"  # vector attention: tensor-core tiles (default) or the CTA-per-point kernel
 
 
@@ -221,10 +223,17 @@ class PTGeometry:
 
     @staticmethod
     def _knn(k, src, qry, o_src, o_qry):
-        m = qry.shape[0]
+        m, n, nb = qry.shape[0], src.shape[0], int(o_src.shape[0])
         idx = torch.empty(m, k, dtype=torch.int32, device=src.device)
         d2 = torch.empty(m, k, dtype=torch.float32, device=src.device)
-        L.call("knn_packed", m, k, L.ptr(src), L.ptr(qry), L.ptr(o_src), L.ptr(o_qry), int(o_src.shape[0]), L.ptr(idx), L.ptr(d2))
+        if KNN_GRID and k in (3, 8, 16):
+            # uniform-grid search with the brute-force results (bit-exact; ties fall back to the literal heap emulation)
+            fn = L.lib().etch_knn_grid_scratch_bytes
+            fn.restype = ctypes.c_longlong
+            scratch = torch.empty(int(fn(n, nb)), dtype=torch.uint8, device=src.device)
+            L.call("knn_grid", m, k, L.ptr(src), n, L.ptr(qry), L.ptr(o_src), L.ptr(o_qry), nb, L.ptr(idx), L.ptr(d2), L.ptr(scratch))
+        else:
+            L.call("knn_packed", m, k, L.ptr(src), L.ptr(qry), L.ptr(o_src), L.ptr(o_qry), nb, L.ptr(idx), L.ptr(d2))
         return idx, d2
 
 

@@ -170,6 +170,12 @@ int etch_so3_inter_conv_v3(const float* xyz, const float* feat, const int* sampl
                            const float* Wc, const float* bias, int B, int q, int P, int nn, int cin, int cout, float sigma,
                            float* g4, float* zraw, double* stats, cudaStream_t stream);
 
+/* kNN with the results of etch_knn_packed (same indices and distances, bit for bit) through a uniform grid over the candidates
+ * of every segment; nsample in {3, 8, 16}; n = rows of xyz.  scratch: caller-owned, etch_knn_grid_scratch_bytes(n, nbatch) bytes. */
+long long etch_knn_grid_scratch_bytes(int n, int nbatch);
+int etch_knn_grid(int m, int nsample, const float* xyz, int n, const float* new_xyz, const int* offset, const int* new_offset,
+                  int nbatch, int* idx, float* dist2, void* scratch, cudaStream_t stream);
+
 /* PointTransformerLayer (pointtransformer_seg.py:8-37) + bn2 + ReLU with the first attention linear as a GEMM over
  * (point, neighbour) rows on tcgen05.  chan [c][8] = {P3 row (3), p3b, s0, h0, so, ho}; W1c [c/64][2][16][max(c/8,16)][4]
  * (TF32 hi/lo canonical tiles of the BN-folded Linear(c, c/8), one per 64-channel chunk); ns in {8, 16}. */

@@ -142,3 +142,48 @@ def test_fps_packed_matches_oracle(cuda, segs, ties):
     p.furthestsampling_cuda(len(segs), max(segs), torch.from_numpy(xyz).to(cuda), torch.from_numpy(off).to(cuda),
                             torch.from_numpy(noff).to(cuda), tmp, idx)
     np.testing.assert_array_equal(idx.cpu().numpy(), O.fps_packed(xyz, off, noff))
+
+
+def _knn_grid(cuda, k, xyz, q, off, noff):
+    import ctypes
+    from etch_b200 import _lib as L
+    n, m = xyz.shape[0], q.shape[0]
+    fn = L.lib().etch_knn_grid_scratch_bytes
+    fn.restype = ctypes.c_longlong
+    scratch = torch.empty(int(fn(n, len(off))), dtype=torch.uint8, device=cuda)
+    idx = torch.zeros(m, k, dtype=torch.int32, device=cuda)
+    d2 = torch.zeros(m, k, dtype=torch.float32, device=cuda)
+    tx, tq, to, tn = (torch.from_numpy(a).to(cuda) for a in (xyz, q, off, noff))   # keep the device copies alive across the call
+    L.call("knn_grid", m, k, L.ptr(tx), n, L.ptr(tq), L.ptr(to), L.ptr(tn), len(off), L.ptr(idx), L.ptr(d2), L.ptr(scratch))
+    torch.cuda.synchronize()
+    del tx, tq, to, tn
+    return idx.cpu().numpy(), d2.cpu().numpy()
+
+
+@pytest.mark.parametrize("k", [3, 8, 16])
+@pytest.mark.parametrize("B,n,ties", [(3, 1000, False), (3, 1000, True), (2, 5000, False), (1, 20000, False)])
+def test_knn_grid_matches_oracle(cuda, k, B, n, ties):
+    """etch_knn_grid (uniform-grid search + exact fallback on ties) == the reference's brute-force heap scan, bit for bit."""
+    xyz, off = _packed(B, n, 2, ties)
+    gi, gd = _knn_grid(cuda, k, xyz, xyz, off, off)
+    ri, rd = O.knn_packed(k, xyz, xyz, off, off)
+    np.testing.assert_array_equal(gi, ri)
+    np.testing.assert_array_equal(gd, rd)
+
+
+def test_knn_grid_cross_levels_short_segments_and_outliers(cuda):
+    """queries from another level, a segment shorter than k, queries far outside the candidates' bounding box"""
+    rng = np.random.default_rng(4)
+    seg = [700, 9, 300]
+    xyz = rng.normal(size=(sum(seg), 3)).astype(np.float32)
+    off = np.cumsum(seg).astype(np.int32)
+    nseg = [s // 4 for s in seg]
+    noff = np.cumsum(nseg).astype(np.int32)
+    q = np.concatenate([xyz[s0:s0 + c] for s0, c in zip(np.concatenate([[0], off[:-1]]), nseg)], 0).copy()
+    q[::7] += np.float32(9.0)      # far outside the grid
+    q[3::11] *= np.float32(0.5)
+    for k in (3, 8, 16):
+        gi, gd = _knn_grid(cuda, k, xyz, q, off, noff)
+        ri, rd = O.knn_packed(k, xyz, q, off, noff)
+        np.testing.assert_array_equal(gi, ri)
+        np.testing.assert_array_equal(gd, rd)
