@@ -644,11 +644,11 @@ __global__ void __launch_bounds__(1024) knn_grid_scan_kernel(const int* __restri
 }
 
 template <int NS>
-__global__ void __launch_bounds__(128) knn_grid_query_kernel(int m, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
+__global__ void __launch_bounds__(64) knn_grid_query_kernel(int m, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                              const int* __restrict__ offset, const int* __restrict__ new_offset, int nbatch,
                                                              const KnnGrid* __restrict__ grids, const int* __restrict__ starts,
                                                              const float4* __restrict__ sorted, int* __restrict__ idx, float* __restrict__ dist2) {
-    const int pt = blockIdx.x * 128 + threadIdx.x;
+    const int pt = blockIdx.x * 64 + threadIdx.x;
     if (pt >= m) return;
     const int b = kg_segment(pt, new_offset, nbatch);
     const int start = b == 0 ? 0 : __ldg(offset + b - 1), end = __ldg(offset + b);
@@ -683,20 +683,27 @@ __global__ void __launch_bounds__(128) knn_grid_query_kernel(int m, const float*
                     }
                     const int crow = (z * g.ny + y) * g.nx;
                     const int s0 = __ldg(st + crow + xa), s1 = __ldg(st + crow + xb + 1);   // consecutive cells are consecutive slots
-                    for (int s = s0; s < s1; ++s) {
-                        const float4 c = __ldg(sorted + s);
-                        const float d = etch_sqdist3(qx - c.x, qy - c.y, qz - c.z);
-                        ++cnt;
-                        if (d < ld[NS - 1] || (d == ld[NS - 1] && false)) {
-                            rej = fminf(rej, ld[NS - 1]);
-                            float cd = d;
-                            int ci = __float_as_int(c.w);
+                    for (int sb = s0; sb < s1; sb += 4) {       // 4 candidates in flight: the walk is bound by load latency
+                        float4 cv[4];
 #pragma unroll
-                            for (int i = 0; i < NS; ++i) {          // sorted insertion by swapping through the list
-                                if (cd < ld[i]) { const float td = ld[i]; const int ti = li[i]; ld[i] = cd; li[i] = ci; cd = td; ci = ti; }
+                        for (int u = 0; u < 4; ++u) cv[u] = __ldg(sorted + min(sb + u, s1 - 1));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (sb + u >= s1) break;
+                            const float4 c = cv[u];
+                            const float d = etch_sqdist3(qx - c.x, qy - c.y, qz - c.z);
+                            ++cnt;
+                            if (d < ld[NS - 1]) {
+                                rej = fminf(rej, ld[NS - 1]);
+                                float cd = d;
+                                int ci = __float_as_int(c.w);
+#pragma unroll
+                                for (int i = 0; i < NS; ++i) {      // sorted insertion by swapping through the list
+                                    if (cd < ld[i]) { const float td = ld[i]; const int ti = li[i]; ld[i] = cd; li[i] = ci; cd = td; ci = ti; }
+                                }
+                            } else {
+                                rej = fminf(rej, d);
                             }
-                        } else {
-                            rej = fminf(rej, d);
                         }
                     }
                 }
@@ -854,10 +861,10 @@ ETCH_API int etch_knn_grid(int m, int nsample, const float* xyz, int n, const fl
     knn_grid_bin_kernel<0><<<etch_cdiv(n, 256), 256, 0, stream>>>(xyz, offset, nbatch, n, grids, starts, sorted);
     knn_grid_scan_kernel<<<nbatch, 1024, 0, stream>>>(offset, grids, starts, cursor);
     knn_grid_bin_kernel<1><<<etch_cdiv(n, 256), 256, 0, stream>>>(xyz, offset, nbatch, n, grids, cursor, sorted);
-    const int grid = etch_cdiv(m, 128);
-    if (nsample == 3) knn_grid_query_kernel<3><<<grid, 128, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
-    else if (nsample == 8) knn_grid_query_kernel<8><<<grid, 128, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
-    else knn_grid_query_kernel<16><<<grid, 128, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
+    const int grid = etch_cdiv(m, 64);
+    if (nsample == 3) knn_grid_query_kernel<3><<<grid, 64, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
+    else if (nsample == 8) knn_grid_query_kernel<8><<<grid, 64, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
+    else knn_grid_query_kernel<16><<<grid, 64, 0, stream>>>(m, xyz, new_xyz, offset, new_offset, nbatch, grids, starts, sorted, idx, dist2);
     ETCH_RETURN_LAST();
 }
 
