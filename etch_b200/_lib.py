@@ -41,7 +41,7 @@ def f32(x):
 
 
 # kernel launches issued per C-ABI call (for bench.py's "gpu_launches" claim); everything not listed launches once
-_LAUNCHES_PER_CALL = {"lbs_forward": 2, "direction_head_tc": 4, "so3_inter_conv_v3": 2, "knn_grid": 6}
+_LAUNCHES_PER_CALL = {"lbs_forward": 2, "direction_head_tc": 4, "so3_inter_conv_v3": 2, "knn_grid": 5}
 launch_count = 0
 _profile = None  # when a dict: name -> [(start_event, end_event), ...]
 
