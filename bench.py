@@ -45,10 +45,15 @@ def _markerset():
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    fallback = dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, which="fallback")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"), which="measured")
-    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, which="fallback")
+        try:
+            d = json.load(open(p))
+            return dict(hbm=float(d["hbm_gbs"]), tensor=float(d["bf16_tflops"]),
+                        tensor_sustained=float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), which="measured")
+        except (OSError, ValueError, KeyError, TypeError):   # unreadable / unexpected layout: say so through the fallback label
+            pass
+    return fallback
 
 
 class ClockSampler:
