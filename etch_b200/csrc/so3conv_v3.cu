@@ -11,11 +11,11 @@
 // lane utilisation x 3 TF32 passes, which is no faster than the FP32 pipes.  So:
 //   * 15 compute warps: thread (a, o, h) owns T[a][8o..8o+7][12h..12h+11].  Per neighbour it needs 8 features (two
 //     conflict-free LDS.128 from a 128B-swizzled TMA tile) and 12 weights (three LDS.128) for 96 FMAs.
-//   * the neighbour rows arrive by 2-D tiled TMA (box 60 anchors x 32 channels, SWIZZLE_128B) into a 3-deep ring; the
+//   * the neighbour rows arrive by 2-D tiled TMA (box 60 anchors x 32 channels, SWIZZLE_128B) into a 2-3 deep ring of 2-4-neighbour chunks; the
 //     per-(a,k,n) weights are generated ONCE per neighbour by all compute threads into a double-buffered tile.
 //   * when a pass over the neighbours ends the 96 accumulators are parked in TMEM (tcgen05.st, 384 columns) and the warps
 //     start the next point at once; while they work on it they pull the parked values back slab by slab (tcgen05.ld), split
-//     them into (hi, lo) TF32 and write the canonical A tile of a 48-column K slab.  Warp 15 streams the matching weight
+//     them into (hi, lo) TF32 and write the canonical A tile of a 48-column K slab.  The control warp streams the matching weight
 //     slab (cp.async.bulk) and issues  A_hi x [W_hi; W_lo]  and  A_lo x W_hi  (UMMA M = 64, N = 2*c_out and c_out), so the
 //     3xTF32 product reads every operand once; the epilogue adds the two column halves of the accumulator.
 // c_in = 64 runs two passes per point (channel halves) that accumulate into the same TMEM tile.
@@ -28,19 +28,8 @@ namespace {
 constexpr int NA = 60;
 constexpr int NK = 24;
 constexpr int NPAIRS = NA * NK;              // 1440 (anchor, kernel point) pairs
-#ifndef V3_FFMA2
-#define V3_FFMA2 0                           // 1: packed fma.rn.f32x2 accumulators (half the FMA issue slots; ptxas spills ~290 B/thread)
-#endif
-#ifndef V3_JJ_UNROLL
-#define V3_JJ_UNROLL 1
-#endif
-constexpr int V3_JJ = V3_JJ_UNROLL;          // neighbours unrolled in the FMA phase
-#ifndef V3_SLEEP
-#define V3_SLEEP 256
-#endif
-#ifndef V3_SMEM_CAP
-#define V3_SMEM_CAP 227
-#endif
+constexpr int V3_JJ = 1;                     // neighbours per FMA-loop iteration (see the loop: unrolling costs ~60 MOVs per chunk)
+constexpr unsigned V3_SLEEP = 256;           // ns the idle control warp sleeps between polls
 constexpr int NBR_SLOT = 8192;               // one neighbour tile: 60 rows x 128 B, padded to the 1 KB swizzle atom
 constexpr int NBR_TX = NA * 128;             // bytes one TMA box delivers
 constexpr int CT = 480;                      // compute threads (15 warps)
@@ -73,19 +62,9 @@ struct V3Cfg {
     static constexpr uint32_t STAT_BYTES = COUT * 16;
     static constexpr size_t smem = 1024 + F_BYTES + W_BYTES + A_BYTES + 2 * WSLAB + KRS_BYTES + Z_BYTES + G_BYTES + NBR_BYTES + STAT_BYTES;
     static_assert(SLAB_GROUP * (NCHUNK / SLAB_EVERY) == NSLAB, "slab schedule covers a pass");
-    static_assert(smem <= V3_SMEM_CAP * 1024, "shared memory budget");
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert(2 * COUT <= PARK_COL, "accumulator columns");
 };
-
-// fp32 -> (hi, lo), hi = x rounded to TF32 (ties away; the integer form of cvt.rna without its NaN/Inf special cases), lo = x - hi
-__device__ __forceinline__ void split_fast(float x, float& hi, float& lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-    lo = x - hi;
-}
-
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
-}
 
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -262,11 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
         const uint32_t tlane = (uint32_t)((wp & 3) * 32) << 16;
         const uint32_t park = tmem + tlane + PARK_COL + (uint32_t)(wp >> 2) * 96;
         const uint32_t a_st = (uint32_t)((3 * o) * A_LBO + a * 16);
-#if V3_FFMA2
-        unsigned long long acc[8][6];                    // T[a][8o + c][12h + 2j, 2j + 1] as packed fp32 pairs
-#else
         float acc[8][12];
-#endif
         uint32_t gc = 0, gs = 0;
         const uint32_t total_chunks = NIT * NCHUNK;
 
@@ -303,8 +278,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
 #pragma unroll
                     for (int j4 = 0; j4 < 3; ++j4) {
                         float4 hi, lo;
-                        split_fast(v[j4 * 4 + 0], hi.x, lo.x); split_fast(v[j4 * 4 + 1], hi.y, lo.y);
-                        split_fast(v[j4 * 4 + 2], hi.z, lo.z); split_fast(v[j4 * 4 + 3], hi.w, lo.w);
+                        umma::split_tf32(v[j4 * 4 + 0], hi.x, lo.x); umma::split_tf32(v[j4 * 4 + 1], hi.y, lo.y);
+                        umma::split_tf32(v[j4 * 4 + 2], hi.z, lo.z); umma::split_tf32(v[j4 * 4 + 3], hi.w, lo.w);
                         *reinterpret_cast<float4*>(dh + j4 * A_LBO) = hi;
                         *reinterpret_cast<float4*>(dh + A_HALF + j4 * A_LBO) = lo;
                     }
@@ -364,13 +339,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
             if (work) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-#if V3_FFMA2
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) acc[c][i] = 0ull;
-#else
 #pragma unroll
                     for (int i = 0; i < 12; ++i) acc[c][i] = 0.f;
-#endif
             }
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
@@ -396,22 +366,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                         const float4 w1 = *reinterpret_cast<const float4*>(ws + jj * NPAIRS + 4);
                         const float4 w2 = *reinterpret_cast<const float4*>(ws + jj * NPAIRS + 8);
                         const float fv[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
-#if V3_FFMA2
-                        const unsigned long long ww[6] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y),
-                                                          pack2(w1.z, w1.w), pack2(w2.x, w2.y), pack2(w2.z, w2.w)};
-#pragma unroll
-                        for (int cc = 0; cc < 8; ++cc) {
-                            const unsigned long long ff = pack2(fv[cc], fv[cc]);
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[cc][i]) : "l"(ff), "l"(ww[i]));
-                        }
-#else
                         const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
                         for (int cc = 0; cc < 8; ++cc)
 #pragma unroll
                             for (int i = 0; i < 12; ++i) acc[cc][i] = fmaf(fv[cc], wv[i], acc[cc][i]);
-#endif
                     }
                     __syncwarp();
                     if (lane == 0) { umma::mbar_arrive(&f_free[sl]); umma::mbar_arrive(&c_done); }
@@ -419,18 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                 }
             }
             if (work) {
-#if V3_FFMA2
-                float av[96];
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc)
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        av[cc * 12 + 2 * i] = __uint_as_float((uint32_t)acc[cc][i]);
-                        av[cc * 12 + 2 * i + 1] = __uint_as_float((uint32_t)(acc[cc][i] >> 32));
-                    }
-#else
                 const float* av = &acc[0][0];
-#endif
                 umma::tmem_st32(park, av);
                 umma::tmem_st32(park + 32, av + 32);
                 umma::tmem_st32(park + 64, av + 64);
