@@ -6,13 +6,17 @@
 
 A *step* is one pass of the hot path over one batch of B scans per GPU (BASELINE.json configs[1]: 5k-point scans,
 batch 8): network forward (encoder + direction / magnitude / marker-confidence heads), post-processing, marker
-extraction, two-stage Levenberg-Marquardt SMPL fit and the final full-mesh LBS.  Scans are independent, so ranks never
-communicate on the data path (weak scaling); the only collectives are the timing barrier and the max over ranks.
+extraction, two-stage Levenberg-Marquardt SMPL fit and the final full-mesh LBS.  Scans are independent, so the path shards
+by scans with no exchange step (weak scaling, 8 scans per GPU).
 
 Prints ONE JSON line on rank 0 ("Measurement" for every field).
-  value    device-resident inputs, per-step CUDA-event time, L2 flushed between timed steps, max over ranks
-  e2e      same metric through the public operator API with pinned HOST buffers: H2D of the scans + D2H of the fitted
-           mesh/parameters inside the timed region
+  value    device-resident inputs, one CUDA-event pair around all K steps (batches overlap on their own streams), a 256 MiB
+           L2-flush write on the batch's stream before every step (inside the events), max over ranks
+  e2e      same metric through the public operator API with pinned HOST buffers inside the timed region.  N = 1: H2D of the
+           scans + D2H of the fitted mesh/parameters.  N > 1: rank 0 owns the global batch -- H2D, one NCCL scatter, the step,
+           one NCCL gather of the packed results, D2H on rank 0
+  parity   the accuracy half of the metric: the cpu_baseline scan through the GPU path vs the oracle (V2V mm, arg-max flips,
+           tightness-vector error); inflight_check: the timed configuration's last batch vs an eager run
   roofline dominant kernel, timed live with CUDA events on the launching stream in a separate instrumented step
   cpu_baseline / --impl reference : the CPU oracle (port of the reference's algorithm; the reference has no CPU path and
            its LM solver is not vendored) timed on this box's host cores on a bounded sample
@@ -101,12 +105,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-LM_SAMPLE_ITERS = (3, 3)  # CPU sample: 3+3 of the 30+50 LM iterations, cost extrapolated linearly (every iteration costs the same)
-
-
-def _oracle_scan_seconds(pts, sd, tables, body_t, vids, n_markers):
-    """CPU seconds for ONE scan through the oracle port: full network forward + post-processing + markers, plus a
-    bounded sample of the 2-stage LM (LM_SAMPLE_ITERS iterations, scaled to the full 30+50) and the final LBS."""
+def _oracle_scan(pts, sd, tables, body_t, vids, n_markers):
+    """ONE scan through the CPU oracle port, nothing extrapolated: full network forward + post-processing + markers, the
+    full two-stage LM (30 + 50 iterations, per-sample convergence test as in the reference) and the final LBS.
+    -> (seconds, seconds_net, seconds_lm, outputs)"""
     from oracle import lm as olm
     from oracle import net as onet
     t0 = time.time()
@@ -116,9 +118,11 @@ def _oracle_scan_seconds(pts, sd, tables, body_t, vids, n_markers):
         mk, valid = olm.get_markers(inner, labels, out["confidences"], n_markers)
     t_net = time.time() - t0
     t0 = time.time()
-    olm.fit(body_t, vids, mk, valid, steps0=LM_SAMPLE_ITERS[0], steps1=LM_SAMPLE_ITERS[1])
-    t_lm = (time.time() - t0) * (30 + 50) / float(sum(LM_SAMPLE_ITERS))
-    return t_net + t_lm, t_net, t_lm
+    hist = []
+    fit = olm.fit(body_t, vids, mk, valid, steps0=30, steps1=50, history=hist)
+    t_lm = time.time() - t0
+    res = dict(out=out, labels=labels, vec=vec, inner=inner, markers=mk, valid=valid, fit=fit, lm_iterations=len(hist))
+    return t_net + t_lm, t_net, t_lm, res
 
 
 def _cpu_threads():
@@ -126,9 +130,24 @@ def _cpu_threads():
     return min(os.cpu_count() or 1, int(os.environ.get("ETCH_CPU_THREADS", "32")))
 
 
+def _workload_config(args, world, in_flight, extra=None):
+    B, N = args.batch, args.points
+    cfg = {"workload": "%dk-pt clothed scans, batch %d per GPU, full net forward + 2-stage LM SMPL fit (BASELINE configs[%d])" % (
+               N // 1000, B, {5000: 1, 10000: 2, 20000: 3}.get(N, 1)),
+           "points": N, "batch_per_gpu": B, "global_batch": B * world,
+           "clouds": "area-weighted samples of the reference's in-tree 4D-Dress scan / its SMPL body pushed out by U(0,3cm), "
+                     "random SO(3) pose, 1 mm jitter (etch_b200.synth.sample_real_scans)",
+           "weights": "seeded random init in the reference state-dict layout, BatchNorm statistics calibrated on real-scan clouds",
+           "body_model": "synthetic SMPL-shaped (6890 verts)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own algorithm on this box's host cores.  The reference has no CPU path and its
-    LM solver (theseus) is not vendored, so this is the oracle port (oracle/, kind = "port"), all host threads."""
+    LM solver (theseus) is not vendored, so this is the oracle port (oracle/, kind = "port"), all host threads.  A step is
+    ONE scan of the workload (a bounded sample of the 8-scan batch), run in full: nothing is extrapolated."""
     if rank != 0:
         return
     from etch_b200 import smpl_model, synth
@@ -143,28 +162,26 @@ def run_reference(args, rank, world):
     body = smpl_model.synthetic_body(0)
     body_t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in body.items()}
     vids = list(ms.values())
-    budget_s = float(os.environ.get("ETCH_REF_BUDGET_S", "200"))
+    budget_s = float(os.environ.get("ETCH_REF_BUDGET_S", "900"))
     t_start = time.time()
-    times = []
-    warm = min(args.warmup, 1)
+    times, nets, lms = [], [], []
+    warm = min(args.warmup, 1)   # the CPU path has nothing to warm beyond the first torch.func trace
     for i in range(warm + args.steps):
-        pts = torch.from_numpy(synth.sample_scans(1, args.points, 100 + i))
-        wall0 = time.time()
-        dt, _, _ = _oracle_scan_seconds(pts, sd, tables, body_t, vids, len(ms))
-        wall = time.time() - wall0
+        pts = torch.from_numpy(synth.sample_real_scans(1, args.points, 100 + i))
+        dt, t_net, t_lm, _ = _oracle_scan(pts, sd, tables, body_t, vids, len(ms))
         if i >= warm:
-            times.append(dt)
-        if time.time() - t_start + wall > budget_s and len(times) >= 1:
+            times.append(dt); nets.append(t_net); lms.append(t_lm)
+        if time.time() - t_start + dt > budget_s and len(times) >= 1:
             break
     ms_step = 1000.0 * float(np.mean(times))
     value = 1000.0 / ms_step  # one scan per step
-    sample = ("1 scan of %d points per step: full net forward + markers, LM timed for %d+%d of 30+50 iterations and scaled "
-              "linearly; %d timed steps, %d torch threads" % (args.points, LM_SAMPLE_ITERS[0], LM_SAMPLE_ITERS[1], len(times), cores))
+    sample = ("1 scan of %d points per step (1 of the batch's %d), run in full: net forward %.1f s + LM 30+50 iterations %.1f s; "
+              "%d timed steps after %d warm-up, %d torch threads" % (args.points, args.batch, float(np.mean(nets)), float(np.mean(lms)),
+                                                                      len(times), warm, cores))
+    cfg = _workload_config(args, 1, 1, {"reference_step": "one scan of the batch per step on the host CPU (bounded sample)"})
     line = {"impl": "reference", "metric": "scans/sec (net fwd + SMPL fit)", "value": value, "unit": "scans/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "5k-pt clothed scans, net forward + 2-stage LM SMPL fit (BASELINE configs[1])", "points": args.points,
-                       "batch_per_step": 1, "note": "CPU oracle port; requested steps=%d capped by a %ds budget" % (args.steps, int(budget_s))},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "extrapolated": False,
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -216,6 +233,32 @@ class Pipeline:
         return self.fitter.submit(pts, device=None if pts.is_cuda else self.device)
 
 
+def _parity_vs_oracle(pipe, pts, res):
+    """GPU (eager, B = 1) against the oracle outputs of the SAME scan: the accuracy half of BASELINE.json's metric."""
+    dev = pipe.device
+    fit = pipe.eager(pts.to(dev))
+    torch.cuda.synchronize()
+    o = res["out"]
+    top2 = o["part_labels"].topk(2, dim=-1).values
+    gap = (top2[..., 0] - top2[..., 1]).numpy()
+    flips = (fit["labels"].cpu() != res["labels"]).numpy()
+    verr = (fit["tightness"].cpu() - res["vec"]).norm(dim=-1).numpy().ravel()
+    valid_o = res["valid"].numpy()
+    same_valid = bool((fit["valid"].cpu().numpy() == valid_o).all())
+    merr = (fit["markers"].cpu() - res["markers"]).norm(dim=-1).numpy()[valid_o]
+    v_o, v_g = res["fit"]["vertices"][0].numpy(), fit["vertices"][0].cpu().numpy()
+    finite = bool(np.isfinite(v_o).all())
+    v2v = float(1000.0 * np.linalg.norm(v_g - v_o, axis=-1).mean()) if finite else None
+    jerr = float(1000.0 * np.linalg.norm(fit["joints"][0].cpu().numpy() - res["fit"]["joints"][0].numpy(), axis=-1).max()) if finite else None
+    return {"scan": "the cpu_baseline scan (1 x %d points), GPU eager vs CPU oracle, full 30+50 LM on both sides" % pts.shape[1],
+            "v2v_mm_vs_oracle": v2v, "joints_max_mm_vs_oracle": jerr, "oracle_fit_finite": finite,
+            "argmax_flips": int(flips.sum()), "argmax_flips_with_top2_gap_above_1e-3": int((flips & (gap > 1e-3)).sum()), "points": int(flips.size),
+            "tightness_median_m": float(np.median(verr)), "tightness_p99_m": float(np.quantile(verr, 0.99)), "tightness_max_abs_m": float(verr.max()),
+            "valid_markers": int(valid_o.sum()), "valid_mask_equal": same_valid,
+            "markers_max_abs_m": float(merr.max()) if merr.size else None, "markers_median_m": float(np.median(merr)) if merr.size else None,
+            "lm_iterations_oracle": int(res["lm_iterations"]), "lm_iterations_gpu": [int(x) for x in fit["iters"][0].cpu().tolist()]}
+
+
 def run_etch(args, rank, world, local_rank):
     from etch_b200 import _lib, build, sharding, synth
     if not torch.cuda.is_available():
@@ -230,7 +273,7 @@ def run_etch(args, rank, world, local_rank):
     in_flight = 1 if args.no_graph else max(1, args.in_flight)
     pipe = Pipeline(device, use_graph=not args.no_graph, in_flight=in_flight)
     n_pool = 4
-    host = [torch.from_numpy(synth.sample_scans(B, N, 50 + rank * 100 + i)).pin_memory() for i in range(n_pool)]
+    host = [torch.from_numpy(synth.sample_real_scans(B, N, 50 + rank * 100 + i)).pin_memory() for i in range(n_pool)]
     dev_in = [h.to(device) for h in host]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # > 126 MB L2
 
@@ -244,7 +287,8 @@ def run_etch(args, rank, world, local_rank):
         pipe.submit(dev_in[i % n_pool])
     barrier()
     # ---- timed region: device-resident inputs; `in_flight` batches run concurrently on their own streams, each flushing
-    # L2 (256 MiB write) on its stream right before its step; CUDA events on the default stream bracket all K steps ----
+    # L2 (256 MiB write) on its stream right before its step (inside the timed region); ONE CUDA-event pair on the default
+    # stream brackets all K steps (the batches overlap, so per-step events would not add up) ----
     sampler = ClockSampler(local_rank)
     sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,39 +297,91 @@ def run_etch(args, rank, world, local_rank):
     t0.record()
     tickets = []
     for i in range(args.steps):
-        # the flush precedes the step on the step's own stream
         tk = pipe.fitter.submit(dev_in[i % n_pool]) if args.no_flush else _submit_flushed(pipe, dev_in[i % n_pool], flush)
         tickets.append(tk)
     for tk in tickets[-in_flight:]:
         tk.result()
     t1.record()
     barrier()
+    last_in = dev_in[(args.steps - 1) % n_pool]
+    last_out = {k: tickets[-1]._out[k].clone() for k in ("vertices", "labels")}
     # kernels launched in the timed region: counted at the C-ABI when eager, = captured kernel nodes x replays with the graph
     launches = (_lib.launch_count - l0) if args.no_graph else pipe.fitter.launches_per_step * args.steps
     total_ms = torch.tensor([float(t0.elapsed_time(t1))], device=device)
     sharding.max_over_ranks(total_ms)
     ms_per_step = total_ms.item() / args.steps
-    # ---- end to end: pinned host scans in, fitted mesh + parameters out, copies inside the timed region (each batch's
-    # H2D, step and D2H are enqueued on that batch's stream) ----
-    out_v = [torch.empty(B, 6890, 3, dtype=torch.float32).pin_memory() for _ in range(in_flight)]
-    out_p = [torch.empty(B, 85, dtype=torch.float32).pin_memory() for _ in range(in_flight)]
-    out_j = [torch.empty(B, 45, 3, dtype=torch.float32).pin_memory() for _ in range(in_flight)]
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    tickets = []
-    for i in range(args.steps):
-        tk = pipe.submit(host[i % n_pool])
-        with torch.cuda.stream(tk.stream):
-            fit = tk._out
-            out_v[i % in_flight].copy_(fit["vertices"], non_blocking=True)
-            out_p[i % in_flight].copy_(fit["params"], non_blocking=True)
-            out_j[i % in_flight].copy_(fit["joints"], non_blocking=True)
-        tickets.append(tk)
-    for tk in tickets[-in_flight:]:
-        cur.wait_stream(tk.stream)
-    e1.record()
-    barrier()
+    # ---- the timed configuration against an eager run of the same batch (in_flight graph copies on in_flight streams) ----
+    ref_last = pipe.eager(last_in)
+    torch.cuda.synchronize()
+    fin = torch.isfinite(ref_last["vertices"]).all(-1).all(-1)
+    inflight_check = {"batches_in_flight": in_flight, "labels_equal": bool((last_out["labels"] == ref_last["labels"]).all()),
+                      "v2v_mm_vs_eager_max": float(((last_out["vertices"] - ref_last["vertices"]).norm(dim=-1).mean(-1))[fin].max().item() * 1000.0)
+                      if bool(fin.any()) else None, "finite_scans": int(fin.sum())}
+    # ---- end to end.  N = 1: pinned host scans in, fitted mesh + parameters out, copies inside the timed region (each batch's
+    # H2D, step and D2H are enqueued on that batch's stream).  N > 1: rank 0 owns the GLOBAL batch in pinned host
+    # memory; per step one H2D + one NCCL scatter of [B,N,3] slices, the step, one NCCL gather of the packed results
+    # (vertices | params | joints) to rank 0 and one D2H there -- all inside the events ----
+    W = sharding.RESULT_WIDTH
+    comm_bytes = None
+    if world == 1:
+        out_rows = [torch.empty(B, W, dtype=torch.float32).pin_memory() for _ in range(in_flight)]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tickets = []
+        for i in range(args.steps):
+            tk = pipe.submit(host[i % n_pool])
+            with torch.cuda.stream(tk.stream):
+                out_rows[i % in_flight].copy_(sharding.pack_results(tk._out), non_blocking=True)
+            tickets.append(tk)
+        for tk in tickets[-in_flight:]:
+            cur.wait_stream(tk.stream)
+        e1.record()
+        barrier()
+    else:
+        comm = torch.cuda.Stream(device=device)
+        ghost = [torch.from_numpy(synth.sample_real_scans(B * world, N, 900 + i)).pin_memory() for i in range(n_pool)] if rank == 0 else None
+        gdev = [torch.empty(B * world, N, 3, dtype=torch.float32, device=device) for _ in range(in_flight)] if rank == 0 else None
+        local_in = [torch.empty(B, N, 3, dtype=torch.float32, device=device) for _ in range(in_flight)]
+        local_rows = [torch.empty(B, W, dtype=torch.float32, device=device) for _ in range(in_flight)]
+        grows = [torch.empty(world, B, W, dtype=torch.float32, device=device) for _ in range(in_flight)] if rank == 0 else None
+        ghost_out = [torch.empty(world, B, W, dtype=torch.float32).pin_memory() for _ in range(in_flight)] if rank == 0 else None
+        pending = []
+
+        def gather(step, tk):
+            k = step % in_flight
+            with torch.cuda.stream(comm):
+                comm.wait_event(tk.done)
+                local_rows[k].copy_(sharding.pack_results(tk._out))
+                sharding.gather_rows(local_rows[k], grows[k] if rank == 0 else None, rank, world)
+                if rank == 0:
+                    ghost_out[k].copy_(grows[k], non_blocking=True)
+
+        def e2e_steps(nsteps):
+            for i in range(nsteps):
+                k = i % in_flight
+                with torch.cuda.stream(comm):
+                    if rank == 0:
+                        gdev[k].copy_(ghost[i % n_pool], non_blocking=True)
+                    sharding.scatter_batch(gdev[k] if rank == 0 else None, local_in[k], rank, world)
+                    got = torch.cuda.Event()
+                    got.record(comm)
+                cur.wait_event(got)                       # submit() orders the slot's stream after the caller's current stream
+                pending.append((i, pipe.fitter.submit(local_in[k])))
+                if len(pending) >= in_flight:             # same order on every rank: scatter(i), gather(i - in_flight + 1)
+                    gather(*pending.pop(0))
+            while pending:
+                gather(*pending.pop(0))
+            cur.wait_stream(comm)
+
+        e2e_steps(in_flight)   # warm the communicator and the staging buffers
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_steps(args.steps)
+        e1.record()
+        barrier()
+        comm_bytes = {"scatter_bytes_per_step": (world - 1) * B * N * 3 * 4, "gather_bytes_per_step": (world - 1) * B * W * 4}
     clocks = sampler.stop()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     sharding.max_over_ranks(e2e_ms)
@@ -303,7 +399,10 @@ def run_etch(args, rank, world, local_rank):
     total_kernel_ms = sum(t for _, t in prof.values())
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     def _algo(name):
-        return ALGO_GFLOP_5K.get(name, ALGO_GFLOP_5K.get(name[:-3] if name.endswith(("_tc", "_v3")) else name))
+        for suf in ("_tc", "_v3", "_v4"):
+            if name.endswith(suf):
+                name = name[:-len(suf)]
+        return ALGO_GFLOP_5K.get(name)
     # dominant kernel = the most expensive one that has a stated algorithmic-work figure (all the big ones do)
     dom, (dom_calls, dom_ms) = next(((k, v) for k, v in top if _algo(k) is not None), top[0])
     scale = N / 5000.0
@@ -324,15 +423,15 @@ def run_etch(args, rank, world, local_rank):
         roofline.update(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s", frac=ach / peaks["tensor"],
                         fp32_simt_peak=fp32_peak, fp32_simt_frac=ach / fp32_peak,
                         peak_source="%s bf16 dense (MEASURED_PEAKS.json burst)" % peaks["which"],
-                        note="algorithmic fp32 flops (SURVEY 8d figure x scans) over the summed launch time of this kernel; its neighbour "
-                             "contraction (half of the flops) is not a dense GEMM and runs on the FP32 pipes (fp32_simt_frac is the same "
-                             "flops against the FP32 SIMT peak), the channel mixing runs as 3xTF32 on tcgen05 (3 MMAs per product, TF32 "
-                             "rate = half of bf16) to keep fp32-level parity")
+                        note="algorithmic fp32 flops (SURVEY 8d figure x scans) over the summed launch time of this kernel; products run "
+                             "as 3xTF32 on tcgen05 (3 MMAs per product, TF32 rate = half of bf16) to keep fp32-level parity, so 1/6 of "
+                             "the bf16 peak is this kernel's ceiling")
     else:
         roofline.update(bound="latency", achieved=None, peak=None, unit=None, frac=None)
     kernels = {k: {"calls": c, "ms": round(t, 4)} for k, (c, t) in top}
-    # ---- CPU baseline: the oracle port on the host cores, one scan (bounded sample) ----
-    cpu_baseline = None
+    # ---- CPU baseline: the oracle port on the host cores, ONE scan run in full after one warm-up scan; the same scan goes
+    # through the GPU path for the accuracy half of the metric (V2V vs the oracle, arg-max flips, tightness error) ----
+    cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:
         from etch_b200 import smpl_model
         from etch_b200.models import spec
@@ -340,25 +439,32 @@ def run_etch(args, rank, world, local_rank):
         torch.set_num_threads(cores)
         sd = synth.make_state_dict(1)
         body_t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in smpl_model.synthetic_body(0).items()}
-        dt, t_net, t_lm = _oracle_scan_seconds(torch.from_numpy(synth.sample_scans(1, N, 100)), sd, spec.so3_tables(), body_t,
-                                               list(pipe.ms.values()), len(pipe.ms))
-        cpu_baseline = {"value": 1.0 / dt, "unit": "scans/s", "cores": cores, "kind": "port",
-                        "sample": "1 scan of %d points: net forward %.1f s + LM %.1f s (timed %d+%d of 30+50 iterations, scaled); "
-                                  "torch-CPU/C oracle, %d threads" % (N, t_net, t_lm, LM_SAMPLE_ITERS[0], LM_SAMPLE_ITERS[1], cores)}
+        tables, vids = spec.so3_tables(), list(pipe.ms.values())
+        _oracle_scan(torch.from_numpy(synth.sample_real_scans(1, N, 99)), sd, tables, body_t, vids, len(pipe.ms))   # warm-up
+        pts1 = torch.from_numpy(synth.sample_real_scans(1, N, 100))
+        dt, t_net, t_lm, res = _oracle_scan(pts1, sd, tables, body_t, vids, len(pipe.ms))
+        cpu_baseline = {"value": 1.0 / dt, "unit": "scans/s", "cores": cores, "kind": "port", "extrapolated": False,
+                        "sample": "1 scan of %d points run in full after 1 warm-up scan: net forward %.1f s + LM 30+50 iterations %.1f s; "
+                                  "torch-CPU/C oracle, %d threads" % (N, t_net, t_lm, cores)}
+        parity = _parity_vs_oracle(pipe, pts1, res)
     scans = B * world
+    e2e = {"value": scans / (e2e_ms_step * 1e-3), "unit": "scans/s", "ms_per_step": e2e_ms_step,
+           "h2d_bytes_per_step": scans * N * 3 * 4, "d2h_bytes_per_step": scans * W * 4}
+    if comm_bytes:
+        e2e.update(comm_bytes)
+        e2e["path"] = "rank 0 pinned host -> H2D -> NCCL scatter -> step on every rank -> NCCL gather -> D2H on rank 0"
+    cfg = _workload_config(args, world, in_flight, {
+        "parallelism": "scan-sharded x%d; value: replicas with device-resident inputs (no data-path collective); e2e: one NCCL scatter + "
+                       "one NCCL gather per step" % world if world > 1 else "single GPU",
+        "l2": "no flush (--no-flush)" if args.no_flush else "256 MiB flush write on the batch's stream before every step (inside the timed region)",
+        "in_flight": in_flight,
+        "timing": "one CUDA-event pair around all K steps (batches overlap, so per-step events would not add up)",
+        "launch": "eager" if args.no_graph else "CUDA graph replay of the step (etch_b200.runtime.ScanFitter)"})
     line = {"metric": "scans/sec (net fwd + SMPL fit)", "value": scans / (ms_per_step * 1e-3), "unit": "scans/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "5k-pt clothed scans, batch 8 per GPU, full net forward + 2-stage LM SMPL fit (BASELINE configs[1])",
-                       "points": N, "batch_per_gpu": B, "global_batch": scans, "parallelism": "scan-sharded x%d (no data-path collective)" % world,
-                       "weights": "seeded random init, reference state-dict layout", "body_model": "synthetic SMPL-shaped (6890 verts)",
-                       "l2": "no flush (--no-flush)" if args.no_flush else "256 MiB flush write on the batch's stream before every step (inside the timed region)",
-                       "in_flight": in_flight,
-                       "timing": "one CUDA-event pair around all K steps (batches overlap, so per-step events would not add up)",
-                       "launch": "eager" if args.no_graph else "CUDA graph replay of the step (etch_b200.runtime.ScanFitter)"},
-            "e2e": {"value": scans / (e2e_ms_step * 1e-3), "unit": "scans/s", "ms_per_step": e2e_ms_step,
-                    "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": B * (6890 * 3 + 85 + 45 * 3) * 4},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels_ms": kernels}
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+            "inflight_check": inflight_check, "kernels_ms": kernels}
     print(json.dumps(line), flush=True)
 
 
@@ -368,13 +474,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="etch", choices=["etch", "reference"])
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--points", type=int, default=5000)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3],
+                    help="BASELINE.json configs[i]: 1 = 8 x 5k per GPU (default, the metric's config), 2 = 16 x 10k, 3 = 8 x 20k per GPU "
+                         "(= 64 scans over 8 GPUs); the mixed stream (configs[4]) is tools/bench_mixed.py")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=5, help="batches in flight (independent graph copies on their own streams)")
     ap.add_argument("--no-flush", action="store_true", help="skip the 256 MiB L2-flush write before every step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     args = ap.parse_args()
+    preset = {1: (8, 5000), 2: (16, 10000), 3: (8, 20000)}[args.config]
+    args.batch = args.batch or preset[0]
+    args.points = args.points or preset[1]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -21,6 +21,11 @@ def lib():
     return _lib
 
 
+class DevPtr(ctypes.c_void_p):
+    """A device pointer that remembers which CUDA device owns it (call() launches on that device and its current stream)."""
+    device_index = None
+
+
 def ptr(t):
     """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
     if t is None:
@@ -29,11 +34,25 @@ def ptr(t):
         raise RuntimeError("etch_b200: expected a CUDA tensor, got device %s" % t.device)
     if not t.is_contiguous():
         raise RuntimeError("etch_b200: tensor must be contiguous")
-    return ctypes.c_void_p(t.data_ptr())
+    p = DevPtr(t.data_ptr())
+    p.device_index = t.device.index
+    return p
 
 
-def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream(device_index=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def _device_of(args):
+    """The one CUDA device all pointer arguments live on (None when a call carries no tensors); mixed devices raise."""
+    dev = None
+    for a in args:
+        if isinstance(a, DevPtr):
+            if dev is None:
+                dev = a.device_index
+            elif a.device_index != dev:
+                raise RuntimeError("etch_b200: arguments live on different CUDA devices (cuda:%d and cuda:%d)" % (dev, a.device_index))
+    return dev
 
 
 def f32(x):
@@ -61,19 +80,29 @@ def stop_profile():
 
 
 def call(name, *args):
-    """Invoke ``int etch_<name>(..., cudaStream_t)`` on the current torch stream; raise on a non-zero status."""
+    """Invoke ``int etch_<name>(..., cudaStream_t)`` on the device that owns the tensor arguments, on that device's current
+    torch stream (like the reference's device-guarded native ops); raise on a non-zero status."""
     global launch_count
     fn = getattr(lib(), "etch_" + name)
     fn.restype = ctypes.c_int
     launch_count += _LAUNCHES_PER_CALL.get(name, 1)
+    dev = _device_of(args)
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call_on_current_device(fn, name, args, dev)
+    return _call_on_current_device(fn, name, args, dev)
+
+
+def _call_on_current_device(fn, name, args, dev):
     if _profile is not None:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        rc = fn(*args, stream())
-        b.record()
+        st = torch.cuda.current_stream(dev)
+        a.record(st)
+        rc = fn(*args, stream(dev))
+        b.record(st)
         _profile.setdefault(name, []).append((a, b))
     else:
-        rc = fn(*args, stream())
+        rc = fn(*args, stream(dev))
     if rc != 0:
         raise RuntimeError("etch_b200: etch_%s failed with status %d (%s)" % (
             name, rc, "invalid argument" if rc == -1 else "unsupported" if rc == -2 else "cudaError"))

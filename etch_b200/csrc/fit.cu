@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(256) markers_kernel(const float* __restrict__ 
             const int k = total < 3 ? total : 3;
             float ws = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
             for (int r = 0; r < k; ++r) {
+                // fewer insertable candidates than labelled points: some confidence is NaN (never inserted above).  torch.topk
+                // ranks NaN first, so the reference's marker is NaN here (fit_SMPL.py:38-51): emit NaN, never read out of bounds
+                if (ti[r] == 0x7fffffff) { sx = sy = sz = ws = __int_as_float(0x7fc00000); break; }
                 const float w = powf(tc[r], 20.0f);
                 const float* p = inner + ((size_t)b * N + ti[r]) * 3;
                 sx += p[0] * w; sy += p[1] * w; sz += p[2] * w; ws += w;

@@ -1,7 +1,14 @@
 """Drop-in for the reference extension ``epn_grouping`` (external/vgtk/vgtk/cuda/grouping_cuda.cpp:176-181)."""
 import torch
 
-from etch_b200 import _lib as L
+import os
+import sys
+
+try:
+    from etch_b200 import _lib as L
+except ImportError:   # only this directory is on sys.path (B2 drop-in use): add the repository root
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from etch_b200 import _lib as L
 
 
 def _check(x, name):

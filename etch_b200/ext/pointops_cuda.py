@@ -1,7 +1,14 @@
 """Drop-in for the reference extension ``pointops_cuda`` (external/pointops/src/pointops_api.cpp:12-23).
 
 Caller allocates the outputs, exactly as src/models/pointops.py:21-23,40-42 does."""
-from etch_b200 import _lib as L
+import os
+import sys
+
+try:
+    from etch_b200 import _lib as L
+except ImportError:   # only this directory is on sys.path (B2 drop-in use): add the repository root
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from etch_b200 import _lib as L
 
 
 def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):

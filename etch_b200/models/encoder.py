@@ -58,7 +58,8 @@ class EncoderPlan:
     def __init__(self, sd, device, input_radius=0.4, n_layers=2):
         self.layers = []
         self.device = device
-        f32 = dict(dtype=torch.float32, device=device)
+        f32 = dict(dtype=torch.float32, device="cpu")   # computed on the host, uploaded once at the end
+        sd = {k: v.detach().cpu() for k, v in sd.items()} if any(v.is_cuda for v in sd.values()) else sd
         for lp in spec.epn_layers(input_radius, n_layers):
             pre = "encoder.backbone.%d.blocks.%d." % (lp["block"], lp["conv"])
             ci, co = lp["dim_in"], lp["dim_out"]
@@ -77,17 +78,17 @@ class EncoderPlan:
                 b_inter=sd[pre + "inter_conv.conv.basic_conv.bias"].to(**f32).reshape(-1).contiguous(),
                 Wt_intra=Wi.view(co, co, 12).permute(2, 1, 0).contiguous(),  # [j][c][o]
                 b_intra=sd[pre + "intra_conv.conv.basic_conv.bias"].to(**f32).reshape(-1).contiguous(),
-                intra_idx=sd[pre + "intra_conv.conv.intra_idx"].to(device=device, dtype=torch.int32).contiguous(),
+                intra_idx=sd[pre + "intra_conv.conv.intra_idx"].to(dtype=torch.int32).contiguous(),
                 Wt_skip=sd[pre + "skip_conv.weight"].to(**f32).view(co, ci).t().contiguous(),  # [c][o]
                 # tensor-core operands: per anchor-neighbour slot j the [c_out x c] slice, TF32-split, canonical tiles
-                Wc_intra=torch.stack([tc.tc_operand(Wi.view(co, co, 12)[:, :, j].cpu(), "cpu") for j in range(12)], 0).contiguous().to(device),
-                Wc_inter=(_inter_slabs(W.cpu(), ci, co).to(device) if ci > 1 else None),
-                Wc_inter3=(_inter_slabs_v3(W.cpu(), ci, co).to(device) if ci > 1 else None),
-                Wc_skip=(tc.tc_operand(sd[pre + "skip_conv.weight"].view(co, ci).cpu(), device)[None].contiguous() if ci > 1 else None),
+                Wc_intra=torch.stack([tc.tc_operand(Wi.view(co, co, 12)[:, :, j].cpu(), "cpu") for j in range(12)], 0).contiguous(),
+                Wc_inter=(_inter_slabs(W.cpu(), ci, co) if ci > 1 else None),
+                Wc_inter3=(_inter_slabs_v3(W.cpu(), ci, co) if ci > 1 else None),
+                Wc_skip=(tc.tc_operand(sd[pre + "skip_conv.weight"].view(co, ci).cpu(), "cpu")[None].contiguous() if ci > 1 else None),
                 b_skip=sd[pre + "skip_conv.bias"].to(**f32).contiguous(),
             )
-            self.layers.append(d)
-        self.anchors = sd["encoder.backbone.0.blocks.0.inter_conv.conv.anchors"].to(**f32).contiguous()
+            self.layers.append({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()})
+        self.anchors = sd["encoder.backbone.0.blocks.0.inter_conv.conv.anchors"].to(**f32).contiguous().to(device)
         self.ident = torch.arange(60, dtype=torch.int32, device=device)
 
 

@@ -23,10 +23,14 @@ _CACHE = {}
 
 
 class SimpleMesh:
-    """Stand-in for trimesh.Trimesh(process=False) when trimesh is not installed: .vertices / .faces / .export(obj)."""
+    """Stand-in for trimesh.Trimesh(process=False) when trimesh is not installed: .vertices / .faces / .copy() / .export(obj)
+    (what src/inference_demo.py:108-116 and src/eval.py:213-230 do with the returned meshes)."""
 
     def __init__(self, vertices, faces):
         self.vertices, self.faces = vertices, faces
+
+    def copy(self):
+        return SimpleMesh(self.vertices.copy(), self.faces.copy())
 
     def export(self, path):
         with open(path, "w") as fh:
@@ -98,10 +102,13 @@ def body_tables(args, gender, device):
         return _CACHE[key]
     if gender not in _BODY_PATHS:
         raise ValueError(f"Unexpected gender: {gender}")
+    # caller-supplied model: the entry keeps a reference to the dict it was built from, so a recycled id() can never hand
+    # another model the wrong tables
     key = (id(model), vids, str(device))
-    if key not in _CACHE:
-        _CACHE[key] = BodyTables(model, vids, device)
-    return _CACHE[key]
+    ent = _CACHE.get(key)
+    if ent is None or ent[0] is not model:
+        ent = _CACHE[key] = (model, BodyTables(model, vids, device))
+    return ent[1]
 
 
 def get_markers(args, inner_points, part_labels, confidences):

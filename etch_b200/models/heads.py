@@ -21,11 +21,34 @@ KNN_GRID = os.environ.get("ETCH_B200_KNN", "grid") == "grid"   # kNN through a u
 PT_ATTN_TC = os.environ.get("ETCH_B200_PT_ATTN", "tc") == "tc"  # vector attention: tensor-core tiles (default) or the CTA-per-point kernel
 
 
+def _upload(obj, device):
+    """Move every tensor reachable from a plan object (attributes, dicts, lists, tuples) to `device`, in place."""
+    if torch.is_tensor(obj):
+        return obj.to(device)
+    if isinstance(obj, dict):
+        for k in obj:
+            obj[k] = _upload(obj[k], device)
+        return obj
+    if isinstance(obj, list):
+        for i in range(len(obj)):
+            obj[i] = _upload(obj[i], device)
+        return obj
+    if isinstance(obj, tuple):
+        return tuple(_upload(o, device) for o in obj)
+    if hasattr(obj, "__dict__") and not isinstance(obj, type):
+        for k, v in vars(obj).items():
+            setattr(obj, k, _upload(v, device))
+    return obj
+
+
+_HOST = dict(dtype=torch.float32, device="cpu")   # plans are computed on the host and uploaded once (_upload)
+
+
 # ----------------------------------------------------------------------------- direction head
 class DirectionPlan:
     def __init__(self, sd, device, anchors):
-        f64 = lambda k: sd[k].detach().to(torch.float64)  # noqa: E731
-        dev = dict(dtype=torch.float32, device=device)
+        f64 = lambda k: sd[k].detach().cpu().to(torch.float64)  # noqa: E731
+        dev = _HOST
 
         def qkv(layer):
             pre = "direction_encoder.self_attention_layers.%d." % layer
@@ -45,7 +68,7 @@ class DirectionPlan:
         self.bf = (w1 @ bc2 + b1).to(**dev)
         self.vreg = (w2.t() @ wr).contiguous().to(**dev)          # [128]      so3_reg o Linear2
         self.creg = float(b2 @ wr + br[0])
-        self.anchors = anchors.reshape(60, 9).contiguous().to(**dev)
+        self.anchors = anchors.detach().cpu().reshape(60, 9).contiguous().to(**dev)
         # tensor-core operands: 9 blocks of 64 output rows x 64 inputs, in consumption order
         #   layer 0: Wq/sqrt(dk), Wk, Wv (2 slices each), head_combine (2); layer 1: Wq/sqrt(dk), Wk, Wv (6); Linear1 o head_combine (4)
         def rows(layer):
@@ -57,7 +80,8 @@ class DirectionPlan:
         assert allrows.shape == (576, 64)
         # 9 blocks of 64 output rows, each split in two K halves (32 inputs): [18][2][8][64][4]
         self.wall = torch.stack([tc.tc_operand(allrows[(i // 2) * 64:(i // 2 + 1) * 64, (i % 2) * 32:(i % 2 + 1) * 32], "cpu")
-                                 for i in range(18)], 0).contiguous().to(device)
+                                 for i in range(18)], 0).contiguous()
+        _upload(self, device)
 
 
 def run_direction(plan, hitpts, xyz2_b3s, feats2, want_anchor_weights=False):
@@ -98,6 +122,10 @@ def _wt(w, dev):
     return w.detach().to(**dev).t().contiguous()
 
 
+def _host_sd(sd):
+    return {k: v.detach().cpu() for k, v in sd.items()} if any(v.is_cuda for v in sd.values()) else sd
+
+
 class _Block:
     def __init__(self, sd, pre, dev):
         d = dev
@@ -129,14 +157,15 @@ class _Block:
         self.chan = torch.cat([self.P3, self.p3b[:, None], self.s0[:, None], self.h0[:, None], self.so[:, None], self.ho[:, None]], 1).contiguous()
         wa = torch.zeros(tp, c)
         wa[:T] = self.Wa.detach().float().cpu()
-        self.Wa_c = torch.stack([tc.tc_operand(wa[:, k:k + 64].contiguous(), "cpu") for k in range(0, c, 64)], 0).contiguous().to(d["device"])
+        self.Wa_c = torch.stack([tc.tc_operand(wa[:, k:k + 64].contiguous(), "cpu") for k in range(0, c, 64)], 0).contiguous()
 
 
 class PTPlan:
     """Folded weights of one PointTransformer (prefix = 'confidence_encoder.' or 'magnitude_encoder.')."""
 
     def __init__(self, sd, prefix, device):
-        d = dict(dtype=torch.float32, device=device)
+        d = _HOST
+        sd = _host_sd(sd)
         self.enc, self.dec = [], []
         for lvl in range(5):
             e = prefix + "enc%d." % (lvl + 1)
@@ -170,7 +199,7 @@ class PTPlan:
             hi, lo = tc.split_tf32(w0)
             # [group l][row u (128)][K quarter kq (4)][k/4 (8)][4] -> [l][kq][k/4][u][4]: one [128 x 32] slice per (group, quarter)
             tile = lambda t: t.view(k, 128, 4, 8, 4).permute(0, 2, 3, 1, 4).reshape(k * 4, 8, 128, 4)  # noqa: E731
-            W0c = torch.stack([tile(hi), tile(lo)], 1).contiguous().to(device)
+            W0c = torch.stack([tile(hi), tile(lo)], 1).contiguous()
             self.head = dict(kind="conf", K=k, W0c=W0c, Wc0t=_wt(sd[prefix + "cls.0.weight"].squeeze(-1), d), sc=s, hc=h,
                              Wc3t=_wt(sd[prefix + "cls.3.weight"].squeeze(-1), d), bc3=sd[prefix + "cls.3.bias"].to(**d).contiguous(),
                              W0t=_wt(sd[prefix + "confi.0.weight"].squeeze(-1), d), b0=sd[prefix + "confi.0.bias"].to(**d).contiguous(),
@@ -180,6 +209,7 @@ class PTPlan:
             s, h = _fold_bn(sd, prefix + "final_layer.1.", d, sd[prefix + "final_layer.0.bias"])
             self.head = dict(kind="mag", W0t=_wt(sd[prefix + "final_layer.0.weight"], d), s=s, h=h,
                              W3t=_wt(sd[prefix + "final_layer.3.weight"], d), b3=sd[prefix + "final_layer.3.bias"].to(**d).contiguous())
+        _upload(self, device)
 
 
 class PTGeometry:
@@ -237,7 +267,13 @@ class PTGeometry:
         return idx, d2
 
 
-_TC_WEIGHTS = {}  # data_ptr of a transposed weight -> its tensor-core block layout (built once per checkpoint/device)
+def _tc_layout(Wt):
+    """tensor-core block layout of a transposed weight, built on first use and kept ON the plan's tensor (freed and rebuilt
+    with the plan: no global cache keyed on pointers)."""
+    ent = getattr(Wt, "_etch_tc", None)
+    if ent is None:
+        ent = Wt._etch_tc = tc.tc_linear_weights(Wt, Wt.device)
+    return ent
 
 
 def _linear(X, Wt, scale=None, shift=None, R=None, relu=False, seg=None, seg_off=None):
@@ -245,11 +281,7 @@ def _linear(X, Wt, scale=None, shift=None, R=None, relu=False, seg=None, seg_off
     co = Wt.shape[1]
     Y = torch.empty(n, co, dtype=torch.float32, device=X.device)
     if USE_TC and ci >= 16 and co >= 16 and ci <= 1024:
-        key = (Wt.data_ptr(), tuple(Wt.shape), str(Wt.device))
-        ent = _TC_WEIGHTS.get(key)
-        if ent is None:
-            wc, nb = tc.tc_linear_weights(Wt, Wt.device)
-            ent = _TC_WEIGHTS[key] = (wc, nb, Wt)  # keep Wt alive so the pointer stays unique
+        ent = _tc_layout(Wt)
         L.call("linear_tc", L.ptr(X), ci, L.ptr(ent[0]), ent[1], n, ci, co, L.ptr(scale), L.ptr(shift), L.ptr(R), L.ptr(seg),
                L.ptr(seg_off), 0 if seg_off is None else int(seg_off.shape[0]), 1 if relu else 0, L.ptr(Y), co)
         return Y

@@ -52,13 +52,21 @@ class GT_network_equiv(nn.Module):
         self._plan = None
         return super().load_state_dict(*a, **k)
 
+    def _weights_version(self):
+        # in-place edits (param.data.copy_, optimizer steps) bump Tensor._version: the folded plan is rebuilt when it changes
+        return sum(t._version for t in self.parameters()) + sum(t._version for t in self.buffers())
+
     def _get_plan(self, device):
-        if self._plan is None or self._plan["device"] != device:
-            sd = self.state_dict()
-            e = enc.EncoderPlan(sd, device, self._radius, self._n_layers)
-            self._plan = dict(device=device, enc=e, dir=heads.DirectionPlan(sd, device, e.anchors),
-                              conf=heads.PTPlan(sd, "confidence_encoder.", device),
-                              mag=heads.PTPlan(sd, "magnitude_encoder.", device))
+        ver = self._weights_version()
+        if self._plan is None or self._plan["device"] != device or self._plan["version"] != ver:
+            # all weight folding (eval BatchNorm -> scale/shift, algebraic fusions, TF32 hi/lo tiles) runs on the HOST in
+            # float64 and the results are uploaded once: no elementwise GPU kernels at plan time
+            sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+            with torch.cuda.device(device):
+                e = enc.EncoderPlan(sd, device, self._radius, self._n_layers)
+                self._plan = dict(device=device, version=ver, enc=e, dir=heads.DirectionPlan(sd, device, e.anchors),
+                                  conf=heads.PTPlan(sd, "confidence_encoder.", device),
+                                  mag=heads.PTPlan(sd, "magnitude_encoder.", device))
         return self._plan
 
     # -- forward ---------------------------------------------------------------------------------

@@ -11,8 +11,10 @@ A step has long latency-bound stretches that leave most of the GPU idle (furthes
 independent copies of the graph (own buffers, own stream) and `submit()` rotates through them, so batch i+1's network
 runs on the SMs batch i's fit leaves idle: +30 % scans/s on a B200 at in_flight=3.  `submit()` returns a Ticket;
 `Ticket.result()` makes the caller's stream wait for that batch and returns its output dict.  The outputs are the slot's
-static tensors: they are overwritten when the slot is reused, `in_flight` submits later.  `fitter(pts)` is
-`submit(pts).result()`.
+static tensors: they are overwritten when the slot is reused, `in_flight` submits later -- `submit()` orders that replay
+after whatever the caller has queued on its current stream at that moment, so reads (clones, D2H copies) issued on the
+caller's stream before the re-submit are safe; reads issued later, or on other streams, are the caller's to order.
+`fitter(pts)` is `submit(pts).result()`.
 """
 import torch
 
@@ -29,7 +31,7 @@ class Ticket:
         """Order the caller's current stream after this batch and return dict(vertices [B,6890,3], joints [B,45,3],
         params [B,85], markers, valid, labels, tightness, inner, confidences, iters, errs)."""
         if self.done is not None:
-            torch.cuda.current_stream().wait_event(self.done)
+            torch.cuda.current_stream(self.stream.device).wait_event(self.done)
         return self._out
 
 
@@ -90,29 +92,36 @@ class ScanFitter:
     @torch.no_grad()
     def submit(self, pts, device=None):
         """pts [B,N,3] float32: a CUDA tensor, or a (pinned) host tensor together with `device` -- the host->device copy then
-        goes straight into a graph's static input buffer on that batch's stream.  Returns a Ticket."""
+        goes straight into a graph's static input buffer on that batch's stream.  Returns a Ticket.  Everything is launched
+        on the device that owns `pts` (or `device`), whatever the thread's current device is."""
         if not pts.is_cuda:
             if device is None:
                 raise RuntimeError("etch_b200 has no CPU path: pass a CUDA tensor, or a host tensor plus the target CUDA device")
             dev = torch.device(device)
             if dev.type != "cuda":
                 raise RuntimeError("etch_b200 has no CPU path: device must be a CUDA device")
-            if not self.use_graph:
-                return Ticket(self._step(pts.to(dev, non_blocking=True)), torch.cuda.current_stream(), None)
-            index = dev.index if dev.index is not None else torch.cuda.current_device()
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
         else:
-            if not self.use_graph:
-                return Ticket(self._step(pts), torch.cuda.current_stream(), None)
-            dev, index = pts.device, pts.device.index
-        key = (tuple(pts.shape), index)
+            dev = pts.device
+        with torch.cuda.device(dev):
+            return self._submit_on(pts, dev)
+
+    def _submit_on(self, pts, dev):
+        if not self.use_graph:
+            return Ticket(self._step(pts if pts.is_cuda else pts.to(dev, non_blocking=True)), torch.cuda.current_stream(dev), None)
+        key = (tuple(pts.shape), dev.index)
         slots = self._slots.get(key)
         if slots is None:
             slots = self._build_slots(key, pts if pts.is_cuda else pts.to(dev))
         i = self._next[key]
         self._next[key] = (i + 1) % len(slots)
         sl = slots[i]
-        if pts.is_cuda:   # order the slot's stream after the producer of pts
-            sl.stream.wait_stream(torch.cuda.current_stream())
+        # Order the slot's stream after everything the caller has queued so far on its current stream of that device: the
+        # producer of a CUDA `pts`, and -- for host input too -- any clone / D2H copy of this slot's previous outputs
+        # (they are static tensors that the replay below overwrites).
+        sl.stream.wait_stream(torch.cuda.current_stream(dev))
+        if pts.is_cuda:
             pts.record_stream(sl.stream)
         with torch.cuda.stream(sl.stream):
             sl.static_in.copy_(pts, non_blocking=True)

@@ -48,6 +48,44 @@ def gather_results(local, total, rank, world):
     return None
 
 
+RESULT_WIDTH = 6890 * 3 + 85 + 45 * 3     # floats per scan in a packed result row: vertices | params (orient, pose, betas, transl) | joints
+
+
+def pack_results(fit):
+    """fit dict of one batch (etch_b200.runtime.ScanFitter output) -> [B, RESULT_WIDTH] contiguous rows, so that the result
+    gather is ONE message per rank (verts + pose + betas + transl + joints, ~84 KB per scan)."""
+    B = fit["vertices"].shape[0]
+    return torch.cat([fit["vertices"].reshape(B, -1), fit["params"].reshape(B, -1), fit["joints"].reshape(B, -1)], 1).contiguous()
+
+
+def unpack_results(rows):
+    """inverse of pack_results for [..., RESULT_WIDTH] rows -> dict(vertices [...,6890,3], params [...,85], joints [...,45,3])."""
+    lead = rows.shape[:-1]
+    nv = 6890 * 3
+    return dict(vertices=rows[..., :nv].reshape(*lead, 6890, 3), params=rows[..., nv:nv + 85],
+                joints=rows[..., nv + 85:].reshape(*lead, 45, 3))
+
+
+def scatter_batch(global_batch, local_out, rank, world):
+    """One collective: rank 0's [world*B, ...] batch (same device type as local_out) -> every rank's [B, ...] slice.
+    NCCL runs it as one grouped send/recv on the current stream; gloo on CPU tensors in the tests."""
+    if world == 1:
+        local_out.copy_(global_batch)
+        return local_out
+    chunks = [c.contiguous() for c in global_batch.chunk(world, 0)] if rank == 0 else None
+    dist.scatter(local_out, chunks, src=0)
+    return local_out
+
+
+def gather_rows(local_rows, global_rows, rank, world):
+    """One collective: every rank's [B, W] rows -> rank 0's [world, B, W] buffer (None elsewhere is fine)."""
+    if world == 1:
+        global_rows[0].copy_(local_rows)
+        return global_rows
+    dist.gather(local_rows, [global_rows[r] for r in range(world)] if rank == 0 else None, dst=0)
+    return global_rows
+
+
 def max_over_ranks(t):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -22,7 +22,22 @@ def _worker(rank, world, port, q):
     out = sharding.gather_results(local.sum(dim=(1, 2), keepdim=False).view(-1, 1), total, rank, world)
     t = torch.tensor([float(rank + 1)])
     mx = sharding.max_over_ranks(t)
+    # the per-step collectives of bench.py --gpus N: one scatter of the global batch, one gather of packed result rows
+    B = 3
+    glob = torch.arange(world * B * 4 * 3, dtype=torch.float32).view(world * B, 4, 3) if rank == 0 else None
+    mine = sharding.scatter_batch(glob, torch.empty(B, 4, 3), rank, world)
+    assert torch.equal(mine, torch.arange(world * B * 12, dtype=torch.float32).view(world * B, 4, 3)[rank * B:(rank + 1) * B])
+    fit = dict(vertices=torch.full((B, 6890, 3), float(rank)), params=torch.arange(B * 85, dtype=torch.float32).view(B, 85) + rank,
+               joints=torch.full((B, 45, 3), 10.0 + rank))
+    rows = sharding.pack_results(fit)
+    assert rows.shape == (B, sharding.RESULT_WIDTH)
+    allrows = torch.empty(world, B, sharding.RESULT_WIDTH) if rank == 0 else None
+    sharding.gather_rows(rows, allrows, rank, world)
     if rank == 0:
+        un = sharding.unpack_results(allrows)
+        ok = all(bool((un["vertices"][r] == float(r)).all()) and bool((un["joints"][r] == 10.0 + r).all())
+                 and torch.equal(un["params"][r], torch.arange(B * 85, dtype=torch.float32).view(B, 85) + r) for r in range(world))
+        assert ok
         q.put((out.view(-1).tolist(), mx.item()))
     dist.barrier()
     dist.destroy_process_group()

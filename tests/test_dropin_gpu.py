@@ -1,0 +1,132 @@
+"""Boundary B1/B2 on the GPU: the reference callers' own call sequence, through the drop-in module NAMES
+(`models.models_pointcloud`, `models.fit_SMPL`, `pointops_cuda`, `epn_grouping`, `epn_gathering`), in a fresh interpreter
+whose PYTHONPATH holds only etch_b200/dropin and etch_b200/ext -- exactly what INTEGRATION.md tells a maintainer to do.
+
+The script below restates src/inference_demo.py:12-17 (load_model), :41-66 (predict_smpl), :108-127 (un-centre, export, npz) and
+the wrapper calls of src/models/pointops.py:10-45 and vgtk/pc/sample.py:58-91 line for line (the reference tree itself does
+not travel to the GPU box)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import argparse, json, os, sys, tempfile
+import numpy as np
+import torch
+from models.models_pointcloud import GT_network_equiv          # src/inference_demo.py:5
+from models.fit_SMPL import fit_smpl                            # src/inference_demo.py:10
+import pointops_cuda, epn_grouping, epn_gathering, epn_zpconv   # src/models/pointops.py:5, vgtk/pc/sample.py:5-6, vgtk/zpconv/functional.py:17
+
+repo = sys.argv[1]
+sys.path.append(repo)      # only for the synthetic checkpoint / body / scan generators (a maintainer has real files instead)
+from etch_b200 import smpl_model, synth
+
+args = argparse.Namespace(gender="neutral", output_folder=tempfile.mkdtemp(), num_point=5000, scale_magnitude=10,
+                          EPN_input_radius=0.4, EPN_layer_num=2)
+args.cuda = torch.cuda.is_available()
+args.device = torch.device("cuda" if args.cuda else "cpu")
+with open(os.path.join(repo, "etch_b200", "data", "superset_smpl.json")) as f:
+    args.markerset = json.load(f)
+args.model_path = os.path.join(args.output_folder, "ckpt.pth")
+torch.save(synth.make_state_dict(1), args.model_path)
+args.smpl_model = smpl_model.synthetic_body(0)      # stands in for datafolder/body_models/smpl/... (licensed, not redistributable)
+
+# ---- load_model (src/inference_demo.py:12-17)
+model = GT_network_equiv(option=args).to(args.device)
+model.load_state_dict(torch.load(args.model_path))
+model.eval()
+assert os.path.exists(os.path.join(args.output_folder, "EPN_model_setting_json"))
+
+# ---- preprocess_scan + sample_points_from_mesh (:19-39) replaced by the committed real-scan cloud; centre as :25-28
+points = synth.sample_real_scan(args.num_point, 5, rotate=False).astype(np.float64)
+original_center = np.array([0.1, -0.2, 0.3])
+
+# ---- predict_smpl (:41-66), verbatim
+with torch.no_grad():
+    points_tensor = torch.from_numpy(points).float().unsqueeze(0).to(args.device)
+    PRED_ITEMS = ["confidence", "direction", "magnitude"]
+    results, selected_indexs = model(points_tensor, pred_items=PRED_ITEMS, direction_mode="standard_vector")
+    pred_part_labels = results["part_labels"]
+    _, pred_part_labels = torch.max(pred_part_labels, -1)
+    pred_confidences = results["confidences"]
+    pred_directions = results["direction"]
+    pred_magnitudes = results["magnitude"]
+    pred_vectors = pred_directions * pred_magnitudes / args.scale_magnitude
+    pred_inner_points = points_tensor - pred_vectors
+    final_mesh_list, _, _, output_smpl_info = fit_smpl(args, pred_inner_points, pred_part_labels, pred_confidences, args.gender)
+pred_smpl_mesh, smpl_info = final_mesh_list[0], output_smpl_info
+
+# ---- main (:107-127)
+pred_smpl_vertices = pred_smpl_mesh.vertices + original_center
+final_smpl_mesh = pred_smpl_mesh.copy()
+final_smpl_mesh.vertices = pred_smpl_vertices
+final_smpl_mesh.export(os.path.join(args.output_folder, "scan_pred_smpl.obj"))
+np.savez(os.path.join(args.output_folder, "scan_output_smpl_info.npz"), body_pose=smpl_info[0][0, :21, :], hand_pose=smpl_info[0][0, 21:23, :],
+         betas=smpl_info[1][0], global_orient=smpl_info[2][0], transl=smpl_info[3][0], joints=smpl_info[4][0])
+assert [d.shape for d in smpl_info] == [(1, 23, 3), (1, 10), (1, 3), (1, 3), (1, 45, 3)]
+assert selected_indexs.shape == (1, 5000, 3) and results["part_labels"].shape == (1, 5000, 86)
+assert np.asarray(pred_smpl_mesh.vertices).shape == (6890, 3) and np.isfinite(pred_smpl_vertices).all()
+try:
+    fit_smpl(args, pred_inner_points, pred_part_labels, pred_confidences, "robot")
+except ValueError:
+    pass
+else:
+    raise AssertionError("unknown gender must raise ValueError (fit_SMPL.py:98-99)")
+
+# ---- the reference's wrapper calls over the B2 names: src/models/pointops.py:10-27 (furthestsampling) and :30-45 (knnquery)
+xyz = points_tensor[0].contiguous()
+offset = torch.cuda.IntTensor([5000]); new_offset = torch.cuda.IntTensor([1250])
+n, b, n_max = xyz.shape[0], offset.shape[0], offset[0]
+for i in range(1, b):
+    n_max = max(offset[i] - offset[i - 1], n_max)
+idx = torch.cuda.IntTensor(new_offset[b - 1].item()).zero_()
+tmp = torch.cuda.FloatTensor(n).fill_(1e10)
+pointops_cuda.furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx)
+new_xyz = xyz[idx.long(), :]
+m = new_xyz.shape[0]
+kidx = torch.cuda.IntTensor(m, 16).zero_(); dist2 = torch.cuda.FloatTensor(m, 16).zero_()
+pointops_cuda.knnquery_cuda(m, 16, xyz, new_xyz, offset, new_offset, kidx, dist2)
+assert idx[0].item() == 0 and len(set(idx.tolist())) == 1250 and (kidx[:, 0] == idx).all() and (dist2[:, 1:] >= dist2[:, :-1]).all()
+# vgtk/pc/sample.py:58-91: furthest_sample -> gather -> ball_query
+pc = points_tensor.permute(0, 2, 1).contiguous()
+sidx = epn_grouping.furthest_point_sampling(pc, 2500)
+new_pc = epn_gathering.gather_points_forward(pc, sidx)
+bidx = epn_grouping.ball_query(new_pc, pc, 0.08, 64)
+assert new_pc.shape == (1, 3, 2500) and bidx.shape == (1, 2500, 64) and bidx.dtype == torch.int32
+torch.cuda.synchronize()
+print("dropin-gpu-ok")
+'''
+
+
+def test_inference_demo_call_sequence_through_dropin_names(cuda, tmp_path):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "etch_b200", "dropin"), os.path.join(ROOT, "etch_b200", "ext")])
+    script = tmp_path / "demo_sequence.py"
+    script.write_text(SCRIPT)
+    r = subprocess.run([sys.executable, str(script), ROOT], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "dropin-gpu-ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
+def test_tensors_on_another_device_than_the_current_one(cuda):
+    """launches follow the tensors' device (and mixed devices raise) instead of the thread's current device."""
+    import torch
+    from etch_b200 import _lib as L
+    from etch_b200.ext import epn_grouping
+    x = torch.randn(1, 3, 256, device=cuda)
+    a = L.ptr(x)
+    assert a.device_index == 0
+    if torch.cuda.device_count() > 1:
+        y = torch.randn(1, 3, 256, device="cuda:1")
+        with pytest.raises(RuntimeError):
+            L.call("ball_query_bcn", L.ptr(x), L.ptr(y), 1, 256, 256, L.f32(0.1), 4, L.ptr(torch.empty(1, 256, 4, dtype=torch.int32, device=cuda)))
+        got = epn_grouping.furthest_point_sampling(y, 64)          # current device is cuda:0, tensors on cuda:1
+        ref = epn_grouping.furthest_point_sampling(y.to(cuda), 64)
+        assert got.device.index == 1 and (got.cpu() == ref.cpu()).all()
+    idx = epn_grouping.furthest_point_sampling(x, 64)
+    assert idx.shape == (1, 64)

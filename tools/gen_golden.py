@@ -4,6 +4,8 @@
                              through tools/ref_shim.py, with the seeded checkpoint etch_b200.synth.make_state_dict(1)
                              loaded by load_state_dict(strict=True) (which also pins the state-dict key layout), on
                              etch_b200.synth.sample_scans(2, 600, seed=5).
+  golden_net_b1_n5000.npz -- the same forward on etch_b200.synth.sample_real_scans(1, 5000, seed=7) (a 5000-point cloud of the
+                             in-tree 4D-Dress scan: the size the metric is quoted on); logits reduced to arg-max/top-2/lse.
   golden_lbs.npz          -- external/smplx/smplx/lbs.py::lbs (+ translation and the 21 extra joints) on the seeded
                              synthetic body etch_b200.smpl_model.synthetic_body(0) with seeded random parameters.
   golden_markers.npz      -- src/models/fit_SMPL.py::get_markers on seeded labels / confidences.
@@ -42,6 +44,20 @@ with torch.inference_mode():
 np.savez_compressed(os.path.join(OUT, "golden_net_b2_n600.npz"), pts=pts.numpy(),
                     **{k: v.numpy().astype(np.float32) for k, v in res.items()}, selected=sel.numpy()[:, :4])
 print("net golden written", {k: tuple(v.shape) for k, v in res.items()})
+
+# the same at the size the metric is quoted on (BASELINE configs[1]: 5000 points), on a cloud of the in-tree real scan; the
+# 86 logits per point are reduced to their arg-max, top-2 values and log-sum-exp to keep the fixture small
+pts5k = torch.from_numpy(synth.sample_real_scans(1, 5000, 7))
+with torch.inference_mode():
+    res5k, _ = net(pts5k, ["confidence", "direction", "magnitude"], "standard_vector")
+lg = res5k["part_labels"][0]
+top2 = lg.topk(2, dim=-1)
+np.savez_compressed(os.path.join(OUT, "golden_net_b1_n5000.npz"), pts=pts5k.numpy(), labels=top2.indices[:, 0].numpy().astype(np.int16),
+                    top2=top2.values.numpy().astype(np.float32), lse=torch.logsumexp(lg, -1).numpy().astype(np.float32),
+                    confidences=res5k["confidences"][0, :, 0].numpy().astype(np.float32),
+                    magnitude=res5k["magnitude"][0, :, 0].numpy().astype(np.float32),
+                    direction=res5k["direction"][0].numpy().astype(np.float32))
+print("net golden (1 x 5000, real scan) written; labels used:", int(np.unique(top2.indices[:, 0].numpy()).size))
 
 # ---------------------------------------------------------------- LBS
 sys.path.insert(0, os.path.join(ref_shim.REF, "external", "smplx"))
