@@ -264,6 +264,8 @@ def run_etch(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl etch needs a CUDA device (there is no CPU fallback); use gpurun")
     build.build()
+    if os.environ.get("ETCH_SM_BUDGET"):     # experiment knob: SMs the persistent kernels fill (default: all 148)
+        _lib.lib().etch_set_sm_budget(int(os.environ["ETCH_SM_BUDGET"]))
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:

@@ -22,9 +22,12 @@
         if (e__ != cudaSuccess) return (int)e__;    \
     } while (0)
 
-// dx*dx + dy*dy + dz*dz exactly as nvcc contracts the reference expression (FMUL, FFMA, FFMA).
+// dx*dx + dy*dy + dz*dz exactly as nvcc contracts the reference expression `(a)*(a) + (b)*(b) + (c)*(c)`: the SECOND product
+// is the plain FMUL and the first is fused onto it -- FMUL(dy,dy), FFMA(dx,dx,.), FFMA(dz,dz,.).  Read off the SASS of the
+// reference's own kernels built for sm_100a (oracle/_ref: knnquery_cuda_kernel.cu:94, sampling_cuda_kernel.cu:53,
+// grouping_cuda_kernel.cu:93,389-390) and pinned by executing them (tests/test_ref_kernels_gpu.py).
 __device__ __forceinline__ float etch_sqdist3(float dx, float dy, float dz) {
-    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 __device__ __forceinline__ float etch_lrelu(float x) { return x > 0.f ? x : 0.01f * x; }

@@ -68,7 +68,7 @@ __device__ __forceinline__ void fps_segment(const FpsSeg& s, int T_ref, float* s
         if (ok) {
             fps_load<PACKED>(s, k, x, y, z);
             if (!PACKED) {  // vgtk variant: points with |p|^2 <= 1e-3 never update temp and never win (:385-387)
-                const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+                const float mag = etch_sqdist3(x, y, z);   // grouping_cuda_kernel.cu:384, same contraction
                 if ((double)mag <= 1e-3) ok = false;
             }
         }
@@ -196,7 +196,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, const int* __restrict__ offset
             fps_load<PACKED>(s, k, x, y, z);
             sx[jl] = x; sy[jl] = y; sz[jl] = z;
             if (!PACKED) {
-                const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+                const float mag = etch_sqdist3(x, y, z);   // grouping_cuda_kernel.cu:384, same contraction
                 if ((double)mag <= 1e-3) ok = false;
             }
         }

@@ -6,8 +6,9 @@
  *   - extern "C", plain device pointers + sizes, no torch types; caller owns all memory; nothing is allocated inside;
  *   - returns 0 on success, a positive cudaError_t on a CUDA failure, ETCH_EINVAL (-1) on a bad argument;
  *   - work is enqueued on `stream` and the call returns immediately (no host synchronisation);
- *   - re-entrant and thread-safe (no global state); pointers must be device memory of the current device, fp32
- *     tensors contiguous in the stated layout.
+ *   - re-entrant and thread-safe; the ONE piece of process-wide state is the tuning knob etch_set_sm_budget (grid size of
+ *     the persistent kernels; set it once at start-up, not per call); pointers must be device memory of the current device,
+ *     fp32 tensors contiguous in the stated layout.
  * File:line citations refer to the reference tree (boqian-li/ETCH) and name the interface each entry replaces.
  * INTEGRATION.md shows the reference-side binding (pybind/ctypes stub) a maintainer would add.
  */
@@ -207,19 +208,17 @@ int etch_linear_tc(const float* X, int ldx, const float* Wc, int NB, int n, int 
                    const float* R, const float* seg, const int* seg_off, int nseg, int relu, float* Y, int ldy,
                    cudaStream_t stream);
 
-/* etch_lm_fit plus SM-clock totals per (scan, phase) in prof (profiling aid for tools/microbench.py). */
-int etch_lm_fit_profile(const float* markers, const unsigned char* valid, const float* Tm, const float* Sm, const float* Pm,
-                        const float* Wm, const float* Jt, const float* Js, const int* parents, const unsigned* ancmask, int B,
-                        int M, int steps0, int steps1, float step0, float step1, float damp0, float damp1, float* params,
-                        int* iters, float* errs, long long* prof, cudaStream_t stream);
+/* ---- mesh -> point cloud in front of the network ------------------------------------------ */
 
-/* tcgen05 building-block self test: C[128,N] = A[128,K] B[N,K]^T (3xTF32); and issue/copy latency probe (tests/, tools/). */
-int etch_umma_selftest(const float* A, const float* B, float* C, int K, int N, cudaStream_t stream);
-int etch_umma_latency(const float* src, long long* out, cudaStream_t stream);
-/* probe: SM cycles for `iters` x 8 warp-level mma.sync.m16n8k8 TF32 per warp, `warps` warps per CTA; out[ctas] */
-int etch_mma_sync_rate(long long* out, int ctas, int warps, int iters, cudaStream_t stream);
-/* probe: SM cycles for `iters` x 32 FP32 FMAs per thread; mode 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
-int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int mode, cudaStream_t stream);
+/* preprocess_scan   src/inference_demo.py:19-34: centre[3] = (min + max) / 2 over verts [V,3] (float64, as trimesh holds them);
+ * centred [V,3] = verts - centre (may be NULL; may alias verts). */
+int etch_mesh_center(const double* verts, int V, double* centre, double* centred, cudaStream_t stream);
+
+/* trimesh.sample.sample_surface   src/inference_demo.py:36-39, src/data_utils/GT_dataloader.py:102 (trimesh itself is an
+ * un-vendored dependency: its published algorithm, restated in float64).  faces [F,3] int32; u_face [count] and u_len [count,2] are
+ * the uniform draws in trimesh's order; scratch [2*F] doubles.  Outputs (each optional): out64 / out32 [count,3], face_index [count]. */
+int etch_mesh_sample(const double* verts, const int* faces, int V, int F, const double* u_face, const double* u_len, int count,
+                     double* scratch, double* out64, float* out32, int* face_index, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

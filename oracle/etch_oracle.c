@@ -33,9 +33,11 @@ int etch_oracle_opt_n_threads(int work_size) {
     return t;
 }
 
-/* (a-b)^2 + (c-d)^2 + (e-f)^2 as nvcc contracts it: FMUL, FFMA, FFMA */
+/* (a)*(a) + (b)*(b) + (c)*(c) as nvcc contracts it in the reference kernels: FMUL(dy,dy), FFMA(dx,dx,.), FFMA(dz,dz,.) --
+ * the SECOND product is the plain multiply.  Read off the SASS of the reference's own .cu files built for sm_100a
+ * (oracle/_ref) and pinned by running them against this emulation on the GPU box (tests/test_ref_kernels_gpu.py). */
 static inline float sqdist3(float dx, float dy, float dz) {
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* tree reduction of grouping_cuda_kernel.cu:339-346,400-460 (and sampling_cuda_kernel.cu:5-10,66-123) */
@@ -70,7 +72,7 @@ void etch_oracle_fps_bcn(const float *xyz, int B, int n, int m, int *idx) {
                 float best = -1.0f;
                 for (int k = tid; k < n; k += T) {
                     const float x2 = X[k], y2 = Y[k], z2 = Z[k];
-                    const float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+                    const float mag = sqdist3(x2, y2, z2);
                     if ((double)mag <= 1e-3) continue; /* origin skip BEFORE the temp update (:385-387) */
                     const float d = sqdist3(x2 - x1, y2 - y1, z2 - z1);
                     const float d2 = d < temp[k] ? d : temp[k];

@@ -329,7 +329,7 @@ def forward(hitpts, sd, tables, input_radius=0.4, n_layers=2, return_trace=False
     p = hitpts.reshape(-1, 3).contiguous()
     x = inv.reshape(B * N, -1).contiguous()
     o = torch.tensor([N * (i + 1) for i in range(B)], dtype=torch.int32)
-    xc, _ = point_transformer_body(p, x, o, sd, "confidence_encoder.")
+    xc, pt_points = point_transformer_body(p, x, o, sd, "confidence_encoder.")
     logits, conf = confidence_head(xc, sd)
     direction, anc_w = direction_head(point_equiv, anchors, sd)
     xm, _ = point_transformer_body(p, x, o, sd, "magnitude_encoder.")
@@ -337,7 +337,8 @@ def forward(hitpts, sd, tables, input_radius=0.4, n_layers=2, return_trace=False
     out = {"confidences": conf.view(B, N, 1), "part_labels": logits.view(B, N, -1), "direction": direction,
            "magnitude": mag.view(B, N, 1)}
     if return_trace:
-        trace.update(up_idx=up_idx, up_w=up_w, inv=inv, anc_w=anc_w.view(B, N, 60), xc=xc, xm=xm, xyz2=xyz2, feats=feats)
+        trace.update(up_idx=up_idx, up_w=up_w, inv=inv, anc_w=anc_w.view(B, N, 60), xc=xc, xm=xm, xyz2=xyz2, feats=feats,
+                     pt_points=pt_points)
         return out, trace
     return out
 

@@ -1,0 +1,101 @@
+"""Mesh -> point cloud (src/inference_demo.py:19-39, src/data_utils/GT_dataloader.py:100-102):
+the CUDA path through the C ABI against the numpy restatement in oracle/mesh_sample.py -- bit-exact (float64 arithmetic,
+same roundings in the same order; face indices are integer work), on the reference's in-tree SMPL body mesh, on a synthetic
+mesh with degenerate / tiny faces, and at 80k faces (the size of the in-tree scan)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mesh_sample as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _smpl_mesh():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mesh_smpl_00122.npz"))
+    return g["vertices"], g["faces"]
+
+
+def _random_mesh(V, F, seed, degenerate=False):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=(V, 3)) * np.array([0.3, 0.9, 0.2])
+    f = rng.integers(0, V, size=(F, 3)).astype(np.int32)
+    if degenerate:
+        f[::7, 1] = f[::7, 0]                 # zero-area faces (repeated vertex): never picked unless pick == cum exactly
+        v[f[3]] = v[f[3, 0]] + 1e-9 * rng.normal(size=(3, 3))    # a tiny face
+    return v, f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["smpl", "random", "degenerate", "80k"])
+def test_sample_surface_bit_exact(cuda, case):
+    from etch_b200 import mesh
+    if case == "smpl":
+        v, f = _smpl_mesh()
+    elif case == "80k":
+        v, f = _random_mesh(40002, 80000, 3)
+    else:
+        v, f = _random_mesh(500, 1500, 1, degenerate=(case == "degenerate"))
+    count = 5000 if case != "80k" else 20000
+    for seed in (15, 16):            # GT_dataloader.py:102 uses seed = self.seed + 15
+        u = O.draws(count, seed)
+        ref_p, ref_f = O.sample_surface(v, f, *u)
+        tv, tf = torch.from_numpy(v).to(cuda), torch.from_numpy(f).to(cuda)
+        p, fi, p32 = mesh.sample_surface(tv, tf, count, seed=seed, want_float32=True)      # draws its own numbers from the same seed
+        np.testing.assert_array_equal(fi.cpu().numpy(), ref_f)
+        np.testing.assert_array_equal(p.cpu().numpy(), ref_p)                              # float64, bit for bit
+        np.testing.assert_array_equal(p32.cpu().numpy(), ref_p.astype(np.float32))         # what torch.from_numpy(points).float() gives
+
+
+@pytest.mark.gpu
+def test_preprocess_scan_bit_exact(cuda):
+    from etch_b200 import mesh
+    v, _ = _smpl_mesh()
+    v = v + np.array([0.3, -1.1, 2.0])
+    ref_v, ref_c = O.preprocess_scan(v)
+    cv, c = mesh.preprocess_scan(v, cuda)
+    np.testing.assert_array_equal(c, ref_c)
+    np.testing.assert_array_equal(cv.cpu().numpy(), ref_v)
+
+
+@pytest.mark.gpu
+def test_scan_to_points_feeds_the_network(cuda, tmp_path):
+    """OBJ file -> centred, sampled float32 cloud on the device -> network forward, without a CPU hop for the geometry."""
+    from etch_b200 import mesh
+    v, f = _smpl_mesh()
+    path = tmp_path / "scan.obj"
+    with open(path, "w") as fh:
+        fh.write("# test\n")
+        for p in v:
+            fh.write("v %.8f %.8f %.8f\n" % tuple(p))
+        for t in f:
+            fh.write("f %d %d %d\n" % tuple(int(i) + 1 for i in t))
+    lv, lf = mesh.load_obj(str(path))
+    np.testing.assert_array_equal(lf, f)
+    assert np.abs(lv - v).max() < 1e-8
+    pts, centre = mesh.scan_to_points(str(path), 5000, cuda, seed=3)
+    ref_v, ref_c = O.preprocess_scan(lv)
+    ref_p, _ = O.sample_surface(ref_v, lf, *O.draws(5000, 3))
+    np.testing.assert_array_equal(centre, ref_c)
+    np.testing.assert_array_equal(pts[0].cpu().numpy(), ref_p.astype(np.float32))
+    assert pts.shape == (1, 5000, 3) and pts.dtype == torch.float32
+
+
+def test_oracle_sampling_properties():
+    """CPU: the restated sampler puts every point on its face (barycentric coordinates in [0,1], summing to 1) and picks faces
+    in proportion to their area."""
+    v, f = _smpl_mesh()
+    u = O.draws(20000, 1)
+    p, fi = O.sample_surface(v, f, *u)
+    a, b, c = v[f[fi, 0]], v[f[fi, 1]], v[f[fi, 2]]
+    T = np.stack([b - a, c - a], -1)                               # [n,3,2]
+    sol = np.stack([np.linalg.lstsq(T[i], p[i] - a[i], rcond=None)[0] for i in range(0, 20000, 40)])
+    assert (sol > -1e-9).all() and (sol.sum(1) < 1 + 1e-9).all()
+    area = O.face_areas(v, f)
+    big = area > np.quantile(area, 0.5)
+    frac = big[fi].mean()
+    assert abs(frac - area[big].sum() / area.sum()) < 0.02
+    cv, centre = O.preprocess_scan(v)
+    assert np.allclose(cv.min(0) + cv.max(0), 0, atol=1e-12) and np.allclose(cv + centre, v)

@@ -162,8 +162,9 @@ def test_layer_constants_match_reference_build_model():
 def test_c_abi_library_exports_every_declared_symbol():
     from etch_b200 import _lib, build
     build.build()
-    header = open(os.path.join(ROOT, "include", "etch_b200.h")).read()
+    header = open(os.path.join(ROOT, "include", "etch_b200.h")).read() + open(os.path.join(ROOT, "include", "etch_b200_probes.h")).read()
     declared = sorted(set(re.findall(r"\b(etch_[a-z0-9_]+)\s*\(", header)))
+    assert "etch_mesh_sample" in declared and "etch_so3_inter_conv_v3" in declared
     assert len(declared) >= 20
     exported = _lib.exported_symbols()
     missing = [s for s in declared if s not in exported]

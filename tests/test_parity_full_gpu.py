@@ -86,8 +86,9 @@ def test_forward_parity_at_baseline_sizes(cuda, N, kind):
         assert e < 4e-4, (li, e)
     # 13 kNN graphs + 4 FPS levels of the PointTransformer hierarchy
     geo = tr["geo"]
-    for lvl, (gi, ri) in enumerate(zip(geo.fps_idx, rt["pt_fps_idx"])):
-        np.testing.assert_array_equal(gi.cpu().numpy(), ri.numpy(), err_msg="pointops FPS level %d" % (lvl + 1))
+    assert len(geo.p) == len(rt["pt_points"]) == 5
+    for lvl, (gp, rp) in enumerate(zip(geo.p, rt["pt_points"])):      # identical FPS picks <=> identical level coordinates
+        np.testing.assert_array_equal(gp.cpu().numpy(), rp.numpy(), err_msg="pointops FPS, level %d" % lvl)
     assert _rel(tr["inv"], rt["inv"]) < 1e-3
     assert _rel(tr["anc_w"], rt["anc_w"]) < 2e-3
     for k in ("part_labels", "confidences", "magnitude"):

@@ -5,6 +5,7 @@ regimes of a real clothed scan although /root/reference does not travel to the G
   scan   [32768,3] f32   samples of datafolder/4D-DRESS/data_processed/model/00122_Inner_Take2_00011/*.obj (the clothed scan)
   body   [32768,3] f32   samples of .../smplh/00122_Inner_Take2_00011/mesh_smpl_*.obj (the SMPL(-H) fit under the clothes)
   body_n [32768,3] f16   unit face normals at the body samples (for the "synthetic clothed" displacement along the normal)
+Also writes tests/golden/mesh_smpl_00122.npz (vertices float64 as parsed from the OBJ, faces int32) for the mesh tests.
 Sampling = face ~ area, then uniform barycentric (u,v) with the sqrt trick (what trimesh.sample.sample_surface does,
 src/inference_demo.py:36-39), numpy.random.default_rng(20240917).  Re-run: python tools/gen_scan_pool.py
 """
@@ -52,6 +53,10 @@ def main():
     out = os.path.join(ROOT, "etch_b200", "data", "scan_pool.npz")
     np.savez_compressed(out, scan=sp.astype(np.float32), body=bp.astype(np.float32), body_n=bn.astype(np.float16))
     print(out, os.path.getsize(out), "bytes; scan bbox", sp.min(0), sp.max(0))
+    # the SMPL(-H) body mesh of the sample as a mesh fixture for the mesh -> point-cloud tests (6890 vertices, 13776 faces)
+    mesh = os.path.join(ROOT, "tests", "golden", "mesh_smpl_00122.npz")
+    np.savez_compressed(mesh, vertices=bv.astype(np.float64), faces=bf.astype(np.int32))
+    print(mesh, os.path.getsize(mesh), "bytes")
 
 
 if __name__ == "__main__":

@@ -22,9 +22,10 @@ for r in rows[hi + 1:end]:
         ln = int(r[0])
     except ValueError:
         continue
-    s = int(r[ci["# Samples"]] or 0)
-    ie = int(r[ci["Instructions Executed"]] or 0)
-    st = sorted(((int(r[ci[c]] or 0), c) for c in stall_cols), reverse=True)[:2]
+    num = lambda v: int(v) if v not in ("", "-") else 0  # noqa: E731
+    s = num(r[ci["# Samples"]])
+    ie = num(r[ci["Instructions Executed"]])
+    st = sorted(((num(r[ci[c]]), c) for c in stall_cols), reverse=True)[:2]
     tot += s
     per.append((s, ie, ln, r[1][:100], st))
 per.sort(reverse=True)
