@@ -249,9 +249,11 @@ def _parity_vs_oracle(pipe, pts, res):
     v_o, v_g = res["fit"]["vertices"][0].numpy(), fit["vertices"][0].cpu().numpy()
     finite = bool(np.isfinite(v_o).all())
     v2v = float(1000.0 * np.linalg.norm(v_g - v_o, axis=-1).mean()) if finite else None
-    jerr = float(1000.0 * np.linalg.norm(fit["joints"][0].cpu().numpy() - res["fit"]["joints"][0].numpy(), axis=-1).max()) if finite else None
+    jd = np.linalg.norm(fit["joints"][0].cpu().numpy() - res["fit"]["joints"][0].numpy(), axis=-1)
+    jerr = float(1000.0 * jd.max()) if finite else None
+    mpjpe = float(1000.0 * jd[:22].mean()) if finite else None      # scripts/experiment_scripts/compute_mpjpe_error.py:23-24: first 22 joints
     return {"scan": "the cpu_baseline scan (1 x %d points), GPU eager vs CPU oracle, full 30+50 LM on both sides" % pts.shape[1],
-            "v2v_mm_vs_oracle": v2v, "joints_max_mm_vs_oracle": jerr, "oracle_fit_finite": finite,
+            "v2v_mm_vs_oracle": v2v, "mpjpe22_mm_vs_oracle": mpjpe, "joints_max_mm_vs_oracle": jerr, "oracle_fit_finite": finite,
             "argmax_flips": int(flips.sum()), "argmax_flips_with_top2_gap_above_1e-3": int((flips & (gap > 1e-3)).sum()), "points": int(flips.size),
             "tightness_median_m": float(np.median(verr)), "tightness_p99_m": float(np.quantile(verr, 0.99)), "tightness_max_abs_m": float(verr.max()),
             "valid_markers": int(valid_o.sum()), "valid_mask_equal": same_valid,

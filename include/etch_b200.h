@@ -220,6 +220,16 @@ int etch_mesh_center(const double* verts, int V, double* centre, double* centred
 int etch_mesh_sample(const double* verts, const int* faces, int V, int F, const double* u_face, const double* u_len, int count,
                      double* scratch, double* out64, float* out32, int* face_index, cudaStream_t stream);
 
+/* ---- evaluation-driver output writers: HOST pointers, no stream ------------------------------ */
+
+/* utils.GT_utils.save_points_with_vector   src/utils/GT_utils.py:22-55 (src/eval.py:147-149): ASCII PLY of n points (red), the n
+ * vector end points hit - vec (blue) and n edges; byte-identical to the reference's Python loop.  style = text form of a float32
+ * inside an f-string: 0 = numpy >= 2 (repr of the widened double), 1 = numpy 1.x (shortest float32 form). */
+int etch_write_points_vector_ply(const char* path, const float* hit_points, const float* vectors, int n, int style);
+
+/* numpy.float32.__str__ for n values, newline separated (formatter self-test used by the CPU suite); returns bytes written, -1 = cap */
+long long etch_format_np_float32(const float* x, int n, int style, char* out, long long cap);
+
 #ifdef __cplusplus
 }
 #endif

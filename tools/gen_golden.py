@@ -119,3 +119,22 @@ mk, valid = ref_get_markers(args, inner, labels, conf)
 np.savez_compressed(os.path.join(OUT, "golden_markers.npz"), inner=inner.numpy(), labels=labels.numpy(), conf=conf.numpy(),
                     markers=mk.numpy(), valid=valid.numpy())
 print("markers golden written", tuple(mk.shape), int(valid.sum()))
+
+# ---------------------------------------------------------------- save_points_with_vector (eval.py output writer)
+# the reference's own function, unmodified, run under THIS interpreter's numpy (its f-string text form of float32 depends on the
+# numpy major version; numpy.__version__ is stored next to the bytes)
+import importlib.util as _ilu  # noqa: E402
+
+_spec = _ilu.spec_from_file_location("ref_gt_utils", os.path.join(ref_shim.REF, "src", "utils", "GT_utils.py"))
+ref_gt_utils = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(ref_gt_utils)
+g = np.random.default_rng(21)
+hit = (g.normal(size=(300, 3)) * np.array([0.3, 0.9, 0.2])).astype(np.float32)
+vec = (g.normal(size=(300, 3)) * 0.03).astype(np.float32)
+hit[0] = [0.0, 1.0, -100000.0]
+vec[0] = [1e-5, -2.5e-7, 0.0]
+hit[1] = [1234567.0, 1e-4, 3.0e16]
+ply = os.path.join(OUT, "golden_points_vector.ply")
+ref_gt_utils.save_points_with_vector(hit, vec, ply)
+np.savez_compressed(os.path.join(OUT, "golden_points_vector_in.npz"), hit=hit, vec=vec, numpy_version=np.__version__)
+print("vector PLY golden written", os.path.getsize(ply), "bytes under numpy", np.__version__)
