@@ -84,3 +84,46 @@ def scan_to_points(path, num_point, device, seed=None):
     cv, centre = preprocess_scan(v, device)
     _, _, p32 = sample_surface(cv, torch.from_numpy(f).to(cv.device), num_point, seed, want_float32=True)
     return p32.unsqueeze(0), centre
+
+
+# ---- ground-truth tightness vectors of the evaluation dataset (src/data_utils/GT_dataloader.py:104-124) ----
+def closest_point(vertices, faces, points):
+    """trimesh.proximity.closest_point(mesh, points) on device buffers: -> (closest [n,3] f64, distance [n] f64, face [n] i32)."""
+    import ctypes
+    dev = vertices.device
+    v = vertices.to(torch.float64).contiguous()
+    f = faces.to(device=dev, dtype=torch.int32).contiguous()
+    p = points.to(device=dev, dtype=torch.float64).contiguous()
+    n, F = int(p.shape[0]), int(f.shape[0])
+    chunks = int(L.lib().etch_mesh_closest_chunks(F))
+    scratch = torch.empty(chunks * n * 12, dtype=torch.uint8, device=dev)
+    closest = torch.empty(n, 3, dtype=torch.float64, device=dev)
+    dist = torch.empty(n, dtype=torch.float64, device=dev)
+    face = torch.empty(n, dtype=torch.int32, device=dev)
+    L.call("mesh_closest_point", L.ptr(v), L.ptr(f), int(v.shape[0]), F, L.ptr(p), n, L.ptr(scratch), L.ptr(closest), L.ptr(dist), L.ptr(face))
+    return closest, dist, face
+
+
+def nearest_point(ref, points):
+    """scipy cKDTree(ref).query(points, k=1): -> (distance [n] f64, index [n] i32)."""
+    dev = ref.device
+    r = ref.to(torch.float64).contiguous()
+    p = points.to(device=dev, dtype=torch.float64).contiguous()
+    n = int(p.shape[0])
+    dist = torch.empty(n, dtype=torch.float64, device=dev)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    L.call("nearest_point", L.ptr(r), int(r.shape[0]), L.ptr(p), n, L.ptr(dist), L.ptr(idx))
+    return dist, idx
+
+
+def gt_vectors(sample_points, info_points, info_vectors, smpl_vertices, smpl_faces, threshold=0.01):
+    """GT_dataloader.py:104-124 on the device (all float64): the info vector of the nearest info point when it is closer than
+    `threshold`, else sample point - closest point on the SMPL mesh.  -> vectors [n,3] f64."""
+    import ctypes
+    p = sample_points.to(torch.float64).contiguous()
+    dists, indices = nearest_point(info_points.to(p.device), p)
+    closest, _, _ = closest_point(smpl_vertices.to(p.device), smpl_faces, p)
+    iv = info_vectors.to(device=p.device, dtype=torch.float64).contiguous()
+    out = torch.empty_like(p)
+    L.call("gt_vectors", L.ptr(p), L.ptr(closest), L.ptr(iv), L.ptr(dists), L.ptr(indices), int(p.shape[0]), ctypes.c_double(threshold), L.ptr(out))
+    return out

@@ -220,6 +220,22 @@ int etch_mesh_center(const double* verts, int V, double* centre, double* centred
 int etch_mesh_sample(const double* verts, const int* faces, int V, int F, const double* u_face, const double* u_len, int count,
                      double* scratch, double* out64, float* out32, int* face_index, cudaStream_t stream);
 
+/* ---- ground-truth tightness vectors of the evaluation dataset (the "VECTORS" block) --------------- */
+
+/* trimesh.proximity.closest_point(smpl_mesh, sample_points)   src/data_utils/GT_dataloader.py:110 (trimesh un-vendored: brute force
+ * over all faces with Ericson's point-triangle projection, float64).  scratch: chunks*n doubles + chunks*n ints with
+ * chunks = etch_mesh_closest_chunks(F).  Outputs: closest [n,3]; dist [n], face [n] optional. */
+int etch_mesh_closest_chunks(int F);
+int etch_mesh_closest_point(const double* verts, const int* faces, int V, int F, const double* pts, int n, void* scratch,
+                            double* closest, double* dist, int* face, cudaStream_t stream);
+
+/* scipy cKDTree(ref).query(pts, k=1)   GT_dataloader.py:106-107: exact nearest neighbour, float64; ties -> lowest index. */
+int etch_nearest_point(const double* ref, int m, const double* pts, int n, double* dist, int* index, cudaStream_t stream);
+
+/* GT_dataloader.py:112-124: vectors = info_vectors[nn_idx] where nn_dist < threshold, else pts - closest. */
+int etch_gt_vectors(const double* pts, const double* closest, const double* info_vectors, const double* nn_dist, const int* nn_idx,
+                    int n, double threshold, double* vectors, cudaStream_t stream);
+
 /* ---- evaluation-driver output writers: HOST pointers, no stream ------------------------------ */
 
 /* utils.GT_utils.save_points_with_vector   src/utils/GT_utils.py:22-55 (src/eval.py:147-149): ASCII PLY of n points (red), the n

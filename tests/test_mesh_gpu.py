@@ -99,3 +99,58 @@ def test_oracle_sampling_properties():
     assert abs(frac - area[big].sum() / area.sum()) < 0.02
     cv, centre = O.preprocess_scan(v)
     assert np.allclose(cv.min(0) + cv.max(0), 0, atol=1e-12) and np.allclose(cv + centre, v)
+
+
+@pytest.mark.gpu
+def test_gt_vectors_block_bit_exact(cuda):
+    """GT_dataloader.py:104-124 (nearest info point, closest point on the SMPL mesh, vector assembly) on the in-tree SMPL body
+    mesh: the CUDA path == the numpy restatement, bit for bit, and the closest points are true minima."""
+    from etch_b200 import mesh
+    v, f = _smpl_mesh()
+    rng = np.random.default_rng(5)
+    n = 600
+    u = O.draws(n, 4)
+    surf, _ = O.sample_surface(v, f, *u)
+    pts = surf + rng.normal(size=(n, 3)) * 0.02              # a clothed-scan-like cloud around the body
+    pts[:5] = surf[:5]                                        # points exactly on the surface
+    pts[5] = v[f[10, 0]]                                      # a mesh vertex (shared by several faces: tie -> same closest point)
+    info_points = pts[::2] + rng.normal(size=(len(pts[::2]), 3)) * 0.006      # ray-cast info points lie near every other sample
+    info_vectors = rng.normal(size=info_points.shape) * 0.03
+    tv, tf = torch.from_numpy(v).to(cuda), torch.from_numpy(f).to(cuda)
+    tp = torch.from_numpy(pts).to(cuda)
+    ref_c, ref_d, ref_f = O.closest_point(v, f, pts)
+    c, d, fi = mesh.closest_point(tv, tf, tp)
+    np.testing.assert_array_equal(c.cpu().numpy(), ref_c)
+    np.testing.assert_array_equal(d.cpu().numpy(), ref_d)
+    same_face = fi.cpu().numpy() == ref_f
+    assert same_face.mean() > 0.99                            # equal distances through adjacent faces may pick either; the point is identical
+    assert ref_d[:6].max() < 1e-12
+    rd, ri = O.nearest_point(info_points, pts)
+    gd, gi = mesh.nearest_point(torch.from_numpy(info_points).to(cuda), tp)
+    np.testing.assert_array_equal(gi.cpu().numpy(), ri)
+    np.testing.assert_array_equal(gd.cpu().numpy(), rd)
+    ref_v = O.gt_vectors(pts, info_points, info_vectors, v, f)
+    got_v = mesh.gt_vectors(tp, torch.from_numpy(info_points).to(cuda), torch.from_numpy(info_vectors).to(cuda), tv, tf)
+    np.testing.assert_array_equal(got_v.cpu().numpy(), ref_v)
+    assert 0.05 < (rd < 0.01).mean() < 0.95                   # both branches of the assembly are exercised
+
+
+def test_oracle_closest_point_is_the_true_minimum():
+    """CPU: the restated projection is no farther than 20000 random barycentric samples of every nearby face, and matches scipy's
+    exact KD-tree for the nearest info point."""
+    from scipy.spatial import cKDTree
+    v, f = _smpl_mesh()
+    rng = np.random.default_rng(2)
+    pts = v[rng.integers(0, len(v), 40)] + rng.normal(size=(40, 3)) * 0.03
+    c, d, fi = O.closest_point(v, f, pts)
+    bary = rng.dirichlet([1, 1, 1], size=300)
+    tri = v[f]                                                 # [F,3,3]
+    for i in range(40):
+        near = np.argsort(np.linalg.norm(tri.mean(1) - pts[i], axis=1))[:60]
+        cand = np.einsum("sk,fkc->fsc", bary, tri[near]).reshape(-1, 3)
+        assert d[i] <= np.linalg.norm(cand - pts[i], axis=1).min() + 1e-12
+        assert abs(np.linalg.norm(c[i] - pts[i]) - d[i]) < 1e-12
+    ref = v[::5]
+    dd, ii = O.nearest_point(ref, pts)
+    sd, si = cKDTree(ref).query(pts, k=1)
+    assert (ii == si).all() and np.allclose(dd, sd, rtol=0, atol=1e-15)

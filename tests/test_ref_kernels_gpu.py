@@ -128,7 +128,12 @@ def test_pointops_knn_three_way(cuda, k, segs, kind):
     m = xyz.shape[0]
     idx = torch.zeros(m, k, dtype=torch.int32, device=cuda)
     d2 = torch.zeros(m, k, dtype=torch.float32, device=cuda)
-    p.knnquery_cuda(m, k, tx, tx, to, to, idx, d2)
+    from etch_b200 import _lib as L
+    L.call("knn_packed", m, k, L.ptr(tx), L.ptr(tx), L.ptr(to), L.ptr(to), int(to.shape[0]), L.ptr(idx), L.ptr(d2))     # brute-force kernel
+    np.testing.assert_array_equal(idx.cpu().numpy(), ri)
+    np.testing.assert_array_equal(d2.cpu().numpy(), rd)
+    idx.zero_(); d2.zero_()
+    p.knnquery_cuda(m, k, tx, tx, to, to, idx, d2)                                                                       # the drop-in binding
     np.testing.assert_array_equal(idx.cpu().numpy(), ri)
     np.testing.assert_array_equal(d2.cpu().numpy(), rd)
     gi, gd = _knn_grid(cuda, k, tx, tx, to, to)
