@@ -484,7 +484,7 @@ def main():
                     help="BASELINE.json configs[i]: 1 = 8 x 5k per GPU (default, the metric's config), 2 = 16 x 10k, 3 = 8 x 20k per GPU "
                          "(= 64 scans over 8 GPUs); the mixed stream (configs[4]) is tools/bench_mixed.py")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=5, help="batches in flight (independent graph copies on their own streams)")
+    ap.add_argument("--in-flight", type=int, default=8, help="batches in flight (independent graph copies on their own streams)")
     ap.add_argument("--no-flush", action="store_true", help="skip the 256 MiB L2-flush write before every step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     args = ap.parse_args()

@@ -113,6 +113,82 @@ def test_inference_demo_call_sequence_through_dropin_names(cuda, tmp_path):
     assert r.returncode == 0 and "dropin-gpu-ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
 
 
+EVAL_SCRIPT = r'''
+import argparse, json, os, sys, tempfile
+import numpy as np
+import torch
+from models.models_pointcloud import GT_network_equiv           # src/eval.py:10
+from models.fit_SMPL import fit_smpl                             # src/eval.py:14
+repo = sys.argv[1]
+sys.path.append(repo)
+from etch_b200 import smpl_model, synth
+from etch_b200.io import save_points_with_vector                 # drop-in for utils.GT_utils.save_points_with_vector (src/eval.py:12)
+
+args = argparse.Namespace(output_folder=tempfile.mkdtemp(), scale_magnitude=10, EPN_input_radius=0.4, EPN_layer_num=2, batch_size=3)
+assert torch.cuda.is_available()                                  # src/eval.py:294
+args.device = torch.device("cuda")
+args.markerset = json.load(open(os.path.join(repo, "etch_b200", "data", "superset_smpl.json")))
+args.smpl_model = smpl_model.synthetic_body(0)
+model = GT_network_equiv(option=args).to(args.device)             # src/eval.py:308-310
+model.load_state_dict(synth.make_state_dict(1))
+model.eval()
+B, N = 3, 5000
+batch = {"hitpts": torch.from_numpy(synth.sample_real_scans(B, N, 11)), "gender": ["male", "male", "female"], "id": ["a", "b", "c"]}
+PRED_ITEMS = ["confidence", "direction", "magnitude"]
+with torch.inference_mode():                                      # src/eval.py:88-116, verbatim
+    hitpts = batch["hitpts"].to(args.device)
+    results, selected_indexs = model(hitpts, PRED_ITEMS, direction_mode="standard_vector")
+    pred_part_labels = results["part_labels"]
+    _, pred_part_labels = torch.max(pred_part_labels, -1)
+    pred_confidences = results["confidences"]
+    pred_directions = results["direction"]
+    pred_magnitudes = results["magnitude"]
+    pred_vectors = pred_directions * pred_magnitudes / args.scale_magnitude
+    hitpts_k = torch.gather(hitpts, 1, selected_indexs)            # :119
+    for j in range(B):                                            # :126-149 (the writer that is ours)
+        os.makedirs(os.path.join(args.output_folder, batch["id"][j]), exist_ok=True)
+        save_points_with_vector(hitpts_k[j].clone().detach().cpu().numpy(), pred_vectors[j].clone().detach().cpu().numpy(),
+                                os.path.join(args.output_folder, batch["id"][j], "hitpts_pred_vectors.ply"))
+with torch.inference_mode():
+    pred_inner_points = hitpts_k - pred_vectors                   # :183
+gender_list = batch["gender"]                                     # :186-209, different genders -> per-sample calls
+final_mesh_list, pred_markers_position, valid_mask, output_smpl_info = [], [], [], [[], [], [], [], []]
+for l, gender in enumerate(gender_list):
+    m_, p_, v_, info_ = fit_smpl(args, pred_inner_points[l].unsqueeze(0), pred_part_labels[l].unsqueeze(0), pred_confidences[l].unsqueeze(0), gender)
+    final_mesh_list.append(m_[0]); pred_markers_position.append(p_[0]); valid_mask.append(v_[0])
+    for i in range(len(info_)):
+        output_smpl_info[i].append(info_[i][0])
+pred_markers_position = torch.stack(pred_markers_position, dim=0)
+valid_mask = torch.stack(valid_mask, dim=0)
+output_smpl_info = [np.stack(info, axis=0) for info in output_smpl_info]
+# the same batch in ONE call (same gender branch, :188-189) must give the same meshes as the per-sample calls
+m_all, p_all, v_all, info_all = fit_smpl(args, pred_inner_points, pred_part_labels, pred_confidences, "male")
+for j in range(B):
+    v2v = np.mean(np.linalg.norm(np.asarray(m_all[j].vertices) - np.asarray(final_mesh_list[j].vertices), axis=1))    # :235-237
+    assert v2v < 1e-6, v2v
+    final_mesh_list[j].export(os.path.join(args.output_folder, batch["id"][j], "forwarded_smpl_mesh_on_pred.obj"))     # :230
+    np.savez(os.path.join(args.output_folder, batch["id"][j], "output_smpl_info.npz"), body_pose=output_smpl_info[0][j][:21, :],
+             hand_pose=output_smpl_info[0][j][21:23, :], betas=output_smpl_info[1][j], global_orient=output_smpl_info[2][j],
+             transl=output_smpl_info[3][j], joints=output_smpl_info[4][j])                                             # :241-247
+assert pred_markers_position.shape == (B, 86, 3) and valid_mask.shape == (B, 86) and valid_mask.dtype == torch.bool
+assert int(valid_mask[0].sum()) > 40
+ply = open(os.path.join(args.output_folder, "a", "hitpts_pred_vectors.ply")).read().split("\n")
+assert ply[2] == "element vertex %d" % (2 * N) and len(ply) == 13 + 3 * N + 1
+print("eval-sequence-ok")
+'''
+
+
+def test_eval_call_sequence_through_dropin_names(cuda, tmp_path):
+    """src/eval.py:88-116,183-209,230-247 (batch forward, per-sample and whole-batch fit, the writers that are ours) in a fresh
+    interpreter with only the drop-in directories on PYTHONPATH."""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "etch_b200", "dropin"), os.path.join(ROOT, "etch_b200", "ext")])
+    script = tmp_path / "eval_sequence.py"
+    script.write_text(EVAL_SCRIPT)
+    r = subprocess.run([sys.executable, str(script), ROOT], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "eval-sequence-ok" in r.stdout, (r.stdout[-1500:], r.stderr[-3000:])
+
+
 def test_tensors_on_another_device_than_the_current_one(cuda):
     """ADVICE r1: launches follow the tensors' device (and mixed devices raise) instead of the thread's current device."""
     import torch

@@ -3,8 +3,8 @@
     python tools/bench_mixed.py [--scans 48] [--batch 8] [--passes 3]            (1 GPU)
     python -m torch.distributed.run --nproc-per-node N tools/bench_mixed.py ...  (N GPUs: the stream is dealt longest-first)
 
-Prints one JSON line (rank 0): scans/s over all ranks, per-size counts, the plan's load imbalance.  Synthetic scans of 5k / 10k /
-20k points (2:1:1), seeded weights; device-resident inputs; time = max over ranks of the CUDA-event time of the timed passes.
+Prints one JSON line (rank 0): scans/s over all ranks, per-size counts, the plan's load imbalance.  Real-scan clouds of 5k / 10k /
+20k points (2:1:1), the seeded calibrated checkpoint; device-resident inputs; time = max over ranks of the CUDA-event time of the timed passes.
 """
 import argparse
 import json
@@ -35,7 +35,7 @@ def main():
     sizes = [(5000, 5000, 10000, 20000)[i % 4] for i in range(a.scans * world)]
     plan = stream.plan_stream(sizes, world, a.batch)
     mine = plan[rank]
-    scans = {i: torch.from_numpy(synth.sample_scan(sizes[i], 500 + i)).to(dev) for _, ids in mine for i in ids}
+    scans = {i: torch.from_numpy(synth.sample_real_scan(sizes[i], 500 + i)).to(dev) for _, ids in mine for i in ids}
     pipe = bench.Pipeline(dev, use_graph=True, in_flight=a.in_flight)
     stream.run_stream(pipe.fitter, scans, mine, dev, pad_to=a.batch)     # warm-up: captures one graph set per point count
     torch.cuda.synchronize()

@@ -21,6 +21,13 @@ from oracle import ref_kernels as R  # noqa: E402
 dev = torch.device("cuda:0")
 REPS = 5
 rows = []
+# bring the clocks up before the first measurement (a fresh box idles at low SM clocks: the first rows were 3x too slow without it)
+_w = torch.randn(4096, 4096, device=dev)
+_t = torch.cuda.Event(enable_timing=True); _u = torch.cuda.Event(enable_timing=True)
+_t.record()
+for _ in range(400):
+    _w = (_w @ _w).clamp_(-1, 1)
+_u.record(); torch.cuda.synchronize()
 
 
 def ours(fn, reps=REPS):
