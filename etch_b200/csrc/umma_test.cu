@@ -205,3 +205,62 @@ ETCH_API int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int 
     else ffma_rate_kernel<1><<<ctas, warps * 32, 0, stream>>>(out, iters, 1.0f);
     ETCH_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Probe for DESIGN.md's "why the neighbour contraction stays on the FP32 pipes": the tensor-core cost of the proposed M = c_in mapping,
+//   D_a[64 x 24] (+)= F_a[64 x 8] * W_a[24 x 8]^T   per (anchor, 8-neighbour K step), 3xTF32 = one N = 48 MMA (A_hi x [W_hi; W_lo])
+//   + one N = 24 MMA (A_lo x W_hi),
+// with every step reading a DIFFERENT operand tile from shared memory (a ring of `ring` (A_hi, A_lo, B) tile sets), as the real kernel
+// would.  One CTA per SM; out[cta] = SM cycles for `steps` steps (both MMAs), measured from first issue to the commit's arrival.
+// mode 0: M = 64, N = 48 + 24 (the proposal); mode 1: M = 128, N = 48 + 24 (two anchors' rows, if they could share B); mode 2: M = 64,
+// N = 128 + 64 (the channel-mixing GEMM of the current kernel at c_out = 64, for scale).
+namespace {
+__global__ void __launch_bounds__(128, 1) umma_contract_probe_kernel(long long* __restrict__ out, int steps, int ring, int mode) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int M = mode == 1 ? 128 : 64, N1 = mode == 2 ? 128 : 48, N2 = mode == 2 ? 64 : 24;
+    const uint32_t a_bytes = (uint32_t)M * 8 * 4, b_bytes = (uint32_t)N1 * 8 * 4;
+    const uint32_t set_bytes = 2 * a_bytes + b_bytes;
+    for (uint32_t i = tid; i < (uint32_t)ring * set_bytes / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 1.0f / (float)(1 + (i & 1023));
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
+    if (tid == 0) umma::mbar_init(&bar, 1);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = umma::uniform(tmem_base);
+    if (warp == 0) {
+        const uint32_t idesc1 = umma::make_idesc_tf32(M, N1), idesc2 = umma::make_idesc_tf32(M, N2);
+        const uint32_t base = umma::smem_u32(smem_raw);
+        const long long t0 = clock64();
+        for (int s = 0; s < steps; ++s) {
+            const uint32_t set = base + (uint32_t)(s % ring) * set_bytes;
+            const uint64_t dah = umma::make_desc(set, (uint32_t)M * 16, 128), dal = umma::make_desc(set + a_bytes, (uint32_t)M * 16, 128);
+            const uint64_t db = umma::make_desc(set + 2 * a_bytes, (uint32_t)N1 * 16, 128);
+            const uint32_t d = tmem + (uint32_t)((s % 2) * 256);       // alternate accumulators so consecutive steps do not serialise on D
+            umma::mma_tf32(d, dah, db, idesc1, s >= 2 ? 1u : 0u);
+            umma::mma_tf32(d, dal, db, idesc2, 1u);
+        }
+        umma::commit(&bar);
+        umma::mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (umma::elect_one()) out[blockIdx.x] = t1 - t0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+
+ETCH_API int etch_umma_contract_probe(long long* out, int ctas, int steps, int ring, int mode, cudaStream_t stream) {
+    if (!out || ctas <= 0 || steps <= 0 || ring <= 0 || mode < 0 || mode > 2) return ETCH_EINVAL;
+    const int M = mode == 1 ? 128 : 64, N1 = mode == 2 ? 128 : 48;
+    const size_t smem = (size_t)ring * (2 * M * 32 + N1 * 32) + 1024;
+    if (smem > 200 * 1024) return ETCH_EINVAL;
+    ETCH_TRY(cudaFuncSetAttribute(umma_contract_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_contract_probe_kernel<<<ctas, 128, smem, stream>>>(out, steps, ring, mode);
+    ETCH_RETURN_LAST();
+}
+

@@ -26,6 +26,10 @@ int etch_mma_sync_rate(long long* out, int ctas, int warps, int iters, cudaStrea
 /* probe: SM cycles for `iters` x 32 FP32 FMAs per thread; mode 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
 int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int mode, cudaStream_t stream);
 
+/* probe: SM cycles for `steps` x (N = 48 + N = 24) tf32 MMAs at M = 64 reading a ring of distinct shared-memory operand tiles -- the tensor-core
+ * cost of the M = c_in mapping of the InterSO3Conv neighbour contraction that DESIGN.md argues against (mode 1: M = 128; mode 2: N = 128 + 64) */
+int etch_umma_contract_probe(long long* out, int ctas, int steps, int ring, int mode, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,9 +93,11 @@ for B, N in ((8, 5000), (16, 10000), (8, 20000)):
         assert torch.equal(ri, ki) and torch.equal(rd, kd)
         t_ref = R.lib().ref_time_knnquery(B * N, k, p(xyz), p(xyz), p(off), p(off), p(ki), p(kd), 3)
         t_grid = ours(grid)
-        t_bf = ours(lambda: pointops_cuda.knnquery_cuda(B * N, k, xyz, xyz, off, off, ki, kd))
-        rows.append(("kNN self-graph k=%d, %d points/scan (grid search, product path)" % (k, N), B, t_ref, t_grid))
-        rows.append(("kNN self-graph k=%d, %d points/scan (brute force, pointops_cuda binding)" % (k, N), B, t_ref, t_bf))
+        def brute():
+            L.call("knn_packed", B * N, k, L.ptr(xyz), L.ptr(xyz), L.ptr(off), L.ptr(off), B, L.ptr(ki), L.ptr(kd))
+        t_bf = ours(brute)
+        rows.append(("kNN self-graph k=%d, %d points/scan (etch_knn_grid: product path and pointops_cuda binding)" % (k, N), B, t_ref, t_grid))
+        rows.append(("kNN self-graph k=%d, %d points/scan (etch_knn_packed: warp-per-query brute force)" % (k, N), B, t_ref, t_bf))
 
 out = ["# Reference CUDA kernels (unmodified, nvcc -O2, sm_100a) vs etch_b200 on the same B200", "",
        "Identical outputs asserted before timing (bit-exact indices and squared distances).  ms per call.", "",
