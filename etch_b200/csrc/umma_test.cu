@@ -215,15 +215,16 @@ ETCH_API int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int 
 // mode 0: M = 64, N = 48 + 24 (the proposal); mode 1: M = 128, N = 48 + 24 (two anchors' rows, if they could share B); mode 2: M = 64,
 // N = 128 + 64 (the channel-mixing GEMM of the current kernel at c_out = 64, for scale).
 namespace {
-__global__ void __launch_bounds__(128, 1) umma_contract_probe_kernel(long long* __restrict__ out, int steps, int ring, int mode) {
+constexpr int CP_RING = 16;
+template <int M, int N1, int N2>
+__global__ void __launch_bounds__(128, 1) umma_contract_probe_kernel(long long* __restrict__ out, int steps) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int M = mode == 1 ? 128 : 64, N1 = mode == 2 ? 128 : 48, N2 = mode == 2 ? 64 : 24;
-    const uint32_t a_bytes = (uint32_t)M * 8 * 4, b_bytes = (uint32_t)N1 * 8 * 4;
-    const uint32_t set_bytes = 2 * a_bytes + b_bytes;
-    for (uint32_t i = tid; i < (uint32_t)ring * set_bytes / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 1.0f / (float)(1 + (i & 1023));
+    constexpr uint32_t a_bytes = (uint32_t)M * 8 * 4, b_bytes = (uint32_t)N1 * 8 * 4;
+    constexpr uint32_t set_bytes = 2 * a_bytes + b_bytes;
+    for (uint32_t i = tid; i < (uint32_t)CP_RING * set_bytes / 4; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 1.0f / (float)(1 + (i & 1023));
     if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
     if (tid == 0) umma::mbar_init(&bar, 1);
     umma::fence_async_smem();
@@ -232,16 +233,19 @@ __global__ void __launch_bounds__(128, 1) umma_contract_probe_kernel(long long* 
     umma::fence_after_sync();
     const uint32_t tmem = umma::uniform(tmem_base);
     if (warp == 0) {
-        const uint32_t idesc1 = umma::make_idesc_tf32(M, N1), idesc2 = umma::make_idesc_tf32(M, N2);
+        constexpr uint32_t idesc1 = umma::make_idesc_tf32(M, N1), idesc2 = umma::make_idesc_tf32(M, N2);
         const uint32_t base = umma::smem_u32(smem_raw);
+        // descriptors of tile set 0; a set is set_bytes further on: only the 14-bit start-address field moves (as in the product kernels)
+        const uint64_t dah0 = umma::make_desc(base, (uint32_t)M * 16, 128), dal0 = umma::make_desc(base + a_bytes, (uint32_t)M * 16, 128);
+        const uint64_t db0 = umma::make_desc(base + 2 * a_bytes, (uint32_t)N1 * 16, 128);
+        constexpr uint64_t inc = set_bytes >> 4;
         const long long t0 = clock64();
+#pragma unroll 8
         for (int s = 0; s < steps; ++s) {
-            const uint32_t set = base + (uint32_t)(s % ring) * set_bytes;
-            const uint64_t dah = umma::make_desc(set, (uint32_t)M * 16, 128), dal = umma::make_desc(set + a_bytes, (uint32_t)M * 16, 128);
-            const uint64_t db = umma::make_desc(set + 2 * a_bytes, (uint32_t)N1 * 16, 128);
-            const uint32_t d = tmem + (uint32_t)((s % 2) * 256);       // alternate accumulators so consecutive steps do not serialise on D
-            umma::mma_tf32(d, dah, db, idesc1, s >= 2 ? 1u : 0u);
-            umma::mma_tf32(d, dal, db, idesc2, 1u);
+            const uint64_t o = (uint64_t)(s & (CP_RING - 1)) * inc;
+            const uint32_t d = tmem + (uint32_t)((s & 1) * 256);       // alternate accumulators so consecutive steps do not serialise on D
+            umma::mma_tf32(d, dah0 + o, db0 + o, idesc1, s >= 2 ? 1u : 0u);
+            umma::mma_tf32(d, dal0 + o, db0 + o, idesc2, 1u);
         }
         umma::commit(&bar);
         umma::mbar_wait(&bar, 0);
@@ -252,15 +256,24 @@ __global__ void __launch_bounds__(128, 1) umma_contract_probe_kernel(long long* 
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
-}  // namespace
 
-ETCH_API int etch_umma_contract_probe(long long* out, int ctas, int steps, int ring, int mode, cudaStream_t stream) {
-    if (!out || ctas <= 0 || steps <= 0 || ring <= 0 || mode < 0 || mode > 2) return ETCH_EINVAL;
-    const int M = mode == 1 ? 128 : 64, N1 = mode == 2 ? 128 : 48;
-    const size_t smem = (size_t)ring * (2 * M * 32 + N1 * 32) + 1024;
-    if (smem > 200 * 1024) return ETCH_EINVAL;
-    ETCH_TRY(cudaFuncSetAttribute(umma_contract_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_contract_probe_kernel<<<ctas, 128, smem, stream>>>(out, steps, ring, mode);
+template <int M, int N1, int N2>
+int launch_contract_probe(long long* out, int ctas, int steps, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)CP_RING * (2 * M * 32 + N1 * 32) + 1024;
+    static_assert(smem <= 200 * 1024, "probe ring");
+    auto kern = umma_contract_probe_kernel<M, N1, N2>;
+    ETCH_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ctas, 128, smem, stream>>>(out, steps);
     ETCH_RETURN_LAST();
 }
+}  // namespace
 
+// mode 0: M = 64, N = 48 + 24 (the proposal); 1: M = 128, N = 48 + 24; 2: M = 64, N = 128 + 64 (channel-mixing GEMM of the shipping kernel,
+// c_out = 64); 3: M = 128, N = 128 + 64; `ring` is fixed at 16 tile sets (argument kept for the ABI, must be 16)
+ETCH_API int etch_umma_contract_probe(long long* out, int ctas, int steps, int ring, int mode, cudaStream_t stream) {
+    if (!out || ctas <= 0 || steps <= 0 || ring != CP_RING || mode < 0 || mode > 3) return ETCH_EINVAL;
+    if (mode == 0) return launch_contract_probe<64, 48, 24>(out, ctas, steps, stream);
+    if (mode == 1) return launch_contract_probe<128, 48, 24>(out, ctas, steps, stream);
+    if (mode == 2) return launch_contract_probe<64, 128, 64>(out, ctas, steps, stream);
+    return launch_contract_probe<128, 128, 64>(out, ctas, steps, stream);
+}

@@ -17,7 +17,8 @@ steps = 4000
 lines = ["# tcgen05 cost of the proposed contraction mapping (measured, 148 CTAs, %d steps each, ring of 16 operand tile sets)" % steps, "",
          "| shape per step | cycles / step (mean over SMs) | per point, nn = 32 (240 steps) | per point, nn = 64 (480 steps) |", "|---|---|---|---|"]
 res = {}
-for mode, name in ((0, "M = 64: N = 48 + N = 24 (the proposal)"), (1, "M = 128: N = 48 + N = 24"), (2, "M = 64: N = 128 + N = 64 (channel-mixing GEMM, c_out = 64)")):
+for mode, name in ((0, "M = 64: N = 48 + N = 24 (the proposal)"), (1, "M = 128: N = 48 + N = 24"), (2, "M = 64: N = 128 + N = 64 (channel-mixing GEMM, c_out = 64)"),
+                   (3, "M = 128: N = 128 + N = 64")):
     for _ in range(2):
         L.call("umma_contract_probe", L.ptr(out), 148, steps, 16, mode)
     torch.cuda.synchronize()
