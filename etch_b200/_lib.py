@@ -63,6 +63,9 @@ def f32(x):
 _LAUNCHES_PER_CALL = {"lbs_forward": 2, "direction_head_tc": 4, "so3_inter_conv_v3": 2, "knn_grid": 5}
 launch_count = 0
 _profile = None  # when a dict: name -> [(start_event, end_event), ...]
+# ETCH_B200_NVTX=1: every C-ABI call is wrapped in an NVTX range named after the entry point (shows up in ncu / nsys timelines; the
+# reference has no tracing at all)
+_NVTX = os.environ.get("ETCH_B200_NVTX", "0") == "1"
 
 
 def start_profile():
@@ -94,7 +97,13 @@ def call(name, *args):
 
 
 def _call_on_current_device(fn, name, args, dev):
-    if _profile is not None:
+    if _NVTX:
+        torch.cuda.nvtx.range_push("etch_" + name)
+        try:
+            rc = fn(*args, stream(dev))
+        finally:
+            torch.cuda.nvtx.range_pop()
+    elif _profile is not None:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st = torch.cuda.current_stream(dev)
         a.record(st)
