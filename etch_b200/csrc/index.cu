@@ -643,6 +643,9 @@ __global__ void __launch_bounds__(1024) knn_grid_scan_kernel(const int* __restri
     if (tid == 1023) st[ncell] = base + s_part[1023];
 }
 
+// diagnostic counters (tools/knn_probe.py): queries answered by the exact brute-force fallback, and candidates visited by the grid walk
+__device__ unsigned long long g_knn_fallbacks = 0ull, g_knn_candidates = 0ull;
+
 template <int NS>
 __global__ void __launch_bounds__(64) knn_grid_query_kernel(int m, const float* __restrict__ xyz, const float* __restrict__ new_xyz,
                                                              const int* __restrict__ offset, const int* __restrict__ new_offset, int nbatch,
@@ -725,6 +728,10 @@ __global__ void __launch_bounds__(64) knn_grid_query_kernel(int m, const float* 
     bool tie = rej <= ld[NS - 1];
 #pragma unroll
     for (int i = 1; i < NS; ++i) tie |= ld[i] == ld[i - 1];
+#ifdef ETCH_KNN_STATS
+    atomicAdd(&g_knn_candidates, (unsigned long long)cnt);
+    if (tie || cnt < NS) atomicAdd(&g_knn_fallbacks, 1ull);
+#endif
     if (tie || cnt < NS) { knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, oi, od); return; }
 #pragma unroll
     for (int i = 0; i < NS; ++i) { oi[i] = li[i]; od[i] = ld[i]; }
@@ -869,3 +876,15 @@ ETCH_API int etch_knn_grid(int m, int nsample, const float* xyz, int n, const fl
 }
 
 ETCH_API int etch_opt_threads(int work_size) { return etch_opt_n_threads(work_size); }
+
+// probe (include/etch_b200_probes.h): reads and resets the kNN-grid diagnostic counters; they only count when the library is built
+// with -DETCH_KNN_STATS (tools/knn_probe.py does that in a scratch copy), out[0] = fallback queries, out[1] = candidates visited
+ETCH_API int etch_knn_grid_stats(unsigned long long* out_host) {
+    if (!out_host) return ETCH_EINVAL;
+    unsigned long long z[2] = {0ull, 0ull};
+    ETCH_TRY(cudaMemcpyFromSymbol(&out_host[0], g_knn_fallbacks, sizeof(unsigned long long)));
+    ETCH_TRY(cudaMemcpyFromSymbol(&out_host[1], g_knn_candidates, sizeof(unsigned long long)));
+    ETCH_TRY(cudaMemcpyToSymbol(g_knn_fallbacks, &z[0], sizeof(unsigned long long)));
+    ETCH_TRY(cudaMemcpyToSymbol(g_knn_candidates, &z[1], sizeof(unsigned long long)));
+    return ETCH_OK;
+}

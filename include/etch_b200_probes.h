@@ -30,6 +30,10 @@ int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int mode, cud
  * cost of the M = c_in mapping of the InterSO3Conv neighbour contraction that DESIGN.md argues against (mode 1: M = 128; mode 2: N = 128 + 64) */
 int etch_umma_contract_probe(long long* out, int ctas, int steps, int ring, int mode, cudaStream_t stream);
 
+/* probe: reads and resets the diagnostic counters of etch_knn_grid (HOST pointer to 2 values: fallback queries, candidates visited); the
+ * counters only tick in a library built with -DETCH_KNN_STATS */
+int etch_knn_grid_stats(unsigned long long* out_host);
+
 #ifdef __cplusplus
 }
 #endif
