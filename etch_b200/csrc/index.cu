@@ -457,6 +457,60 @@ __device__ __noinline__ void knn_serial_exact(int start, int end, float qx, floa
     for (int i = 0; i < NS; ++i) { out_idx[i] = best_idx[i]; out_d[i] = best_dist[i]; }
 }
 
+// The same literal emulation, executed by a whole (converged) warp for ONE query with warp-uniform arguments: the 32 lanes compute
+// the distances of 256 consecutive candidates into `buf` (shared memory, 256 floats owned by this warp), and lane 0 replays them in
+// index order against its heap -- but only when some candidate of the chunk beats the heap root as it stood at the start of the
+// chunk (the root only shrinks, so a chunk without such a candidate cannot change the heap).  After the first few chunks almost
+// every chunk is skipped: a 5000-point fallback costs ~10 us instead of the ~550 us of the one-thread scan, which used to set the
+// duration of the whole kernel as soon as a single query of the batch met a tie.
+constexpr int KNNX_CHUNK = 256;
+template <int NS>
+__device__ __noinline__ void knn_exact_warp(int start, int end, float qx, float qy, float qz, const float* __restrict__ xyz,
+                                            int* __restrict__ out_idx, float* __restrict__ out_d, float* buf) {
+    const int lane = threadIdx.x & 31;
+    float best_dist[NS];
+    int best_idx[NS];
+    for (int i = 0; i < NS; ++i) { best_dist[i] = 1e10f; best_idx[i] = start; }
+    float root = 1e10f;                     // warp-uniform copy of lane 0's heap root
+    for (int c0 = start; c0 < end; c0 += KNNX_CHUNK) {
+        const int cnt = min(KNNX_CHUNK, end - c0);
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < KNNX_CHUNK / 32; ++u) {
+            const int j = u * 32 + lane;
+            if (j < cnt) {
+                const size_t i = (size_t)(c0 + j) * 3;
+                const float d2 = etch_sqdist3(qx - __ldg(xyz + i), qy - __ldg(xyz + i + 1), qz - __ldg(xyz + i + 2));
+                buf[j] = d2;
+                hit |= d2 < root;
+            }
+        }
+        if (__any_sync(0xffffffffu, hit)) {
+            __syncwarp();
+            if (lane == 0) {
+                for (int j = 0; j < cnt; ++j) {
+                    const float d2 = buf[j];
+                    if (d2 < best_dist[0]) {
+                        best_dist[0] = d2;
+                        best_idx[0] = c0 + j;
+                        knn_reheap<NS>(best_dist, best_idx, NS);
+                    }
+                }
+            }
+            root = __shfl_sync(0xffffffffu, best_dist[0], 0);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (int i = NS - 1; i > 0; i--) {
+            const float tf = best_dist[0]; best_dist[0] = best_dist[i]; best_dist[i] = tf;
+            const int ti = best_idx[0]; best_idx[0] = best_idx[i]; best_idx[i] = ti;
+            knn_reheap<NS>(best_dist, best_idx, i);
+        }
+        for (int i = 0; i < NS; ++i) { out_idx[i] = best_idx[i]; out_d[i] = best_dist[i]; }
+    }
+}
+
 constexpr int KNNW_TILE = 1024;   // candidates staged per step (SoA, 12 KB)
 constexpr int KNNW_WARPS = 8;
 
@@ -466,6 +520,7 @@ __global__ void __launch_bounds__(KNNW_WARPS * 32) knn_warp_kernel(int m, const 
                                                                    int nbatch, int* __restrict__ idx, float* __restrict__ dist2) {
     static_assert(NS >= 1 && NS <= 32, "one list entry per lane");
     __shared__ float tx[KNNW_TILE], ty[KNNW_TILE], tz[KNNW_TILE];
+    __shared__ float s_exact[KNNW_WARPS][KNNX_CHUNK];
     __shared__ int s_lo, s_hi;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * KNNW_WARPS + warp;
@@ -525,8 +580,8 @@ __global__ void __launch_bounds__(KNNW_WARPS * 32) knn_warp_kernel(int m, const 
         }
     }
     if (!active) return;
-    if (tie) {
-        if (lane == 0) knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, idx + (size_t)pt * NS, dist2 + (size_t)pt * NS);
+    if (tie) {   // warp-uniform
+        knn_exact_warp<NS>(start, end, qx, qy, qz, xyz, idx + (size_t)pt * NS, dist2 + (size_t)pt * NS, s_exact[warp]);
         return;
     }
     if (lane < NS) {
@@ -651,14 +706,17 @@ __global__ void __launch_bounds__(64) knn_grid_query_kernel(int m, const float* 
                                                              const int* __restrict__ offset, const int* __restrict__ new_offset, int nbatch,
                                                              const KnnGrid* __restrict__ grids, const int* __restrict__ starts,
                                                              const float4* __restrict__ sorted, int* __restrict__ idx, float* __restrict__ dist2) {
+    __shared__ float s_exact[2][KNNX_CHUNK];
     const int pt = blockIdx.x * 64 + threadIdx.x;
-    if (pt >= m) return;
-    const int b = kg_segment(pt, new_offset, nbatch);
+    const bool active = pt < m;
+    const int ptc = active ? pt : m - 1;                 // inactive lanes of the last block shadow the last query and write nothing
+    const int b = kg_segment(ptc, new_offset, nbatch);
     const int start = b == 0 ? 0 : __ldg(offset + b - 1), end = __ldg(offset + b);
-    const float qx = __ldg(new_xyz + (size_t)pt * 3), qy = __ldg(new_xyz + (size_t)pt * 3 + 1), qz = __ldg(new_xyz + (size_t)pt * 3 + 2);
-    int* oi = idx + (size_t)pt * NS;
-    float* od = dist2 + (size_t)pt * NS;
-    if (end - start < NS) { knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, oi, od); return; }
+    const float qx = __ldg(new_xyz + (size_t)ptc * 3), qy = __ldg(new_xyz + (size_t)ptc * 3 + 1), qz = __ldg(new_xyz + (size_t)ptc * 3 + 2);
+    int* oi = idx + (size_t)ptc * NS;
+    float* od = dist2 + (size_t)ptc * NS;
+    bool need_exact = active && (end - start < NS);      // short segment: the reference's (1e10, start) fillers come out of the heap emulation
+    const bool walk = active && !need_exact;
     const KnnGrid g = grids[b];
     const int* st = starts + (size_t)b * (KG_MAXCELLS + 1);
     const int cx = kg_cell_coord(qx, g.ox, g.inv_h, g.nx), cy = kg_cell_coord(qy, g.oy, g.inv_h, g.ny), cz = kg_cell_coord(qz, g.oz, g.inv_h, g.nz);
@@ -668,7 +726,7 @@ __global__ void __launch_bounds__(64) knn_grid_query_kernel(int m, const float* 
     for (int i = 0; i < NS; ++i) { ld[i] = 3e38f; li[i] = start; }
     float rej = 3e38f;      // smallest distance that is NOT in the list
     int cnt = 0;
-    const int rmax = max(g.nx, max(g.ny, g.nz));
+    const int rmax = walk ? max(g.nx, max(g.ny, g.nz)) : -1;
     for (int r = 0; r <= rmax; ++r) {
         const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1), y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
         const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
@@ -728,13 +786,26 @@ __global__ void __launch_bounds__(64) knn_grid_query_kernel(int m, const float* 
     bool tie = rej <= ld[NS - 1];
 #pragma unroll
     for (int i = 1; i < NS; ++i) tie |= ld[i] == ld[i - 1];
+    if (walk) {
 #ifdef ETCH_KNN_STATS
-    atomicAdd(&g_knn_candidates, (unsigned long long)cnt);
-    if (tie || cnt < NS) atomicAdd(&g_knn_fallbacks, 1ull);
+        atomicAdd(&g_knn_candidates, (unsigned long long)cnt);
+        if (tie || cnt < NS) atomicAdd(&g_knn_fallbacks, 1ull);
 #endif
-    if (tie || cnt < NS) { knn_serial_exact<NS>(start, end, qx, qy, qz, xyz, oi, od); return; }
+        if (tie || cnt < NS) need_exact = true;
+        else {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) { oi[i] = li[i]; od[i] = ld[i]; }
+            for (int i = 0; i < NS; ++i) { oi[i] = li[i]; od[i] = ld[i]; }
+        }
+    }
+    // the rare queries that need the literal emulation are served one after the other by the whole warp
+    unsigned todo = __ballot_sync(0xffffffffu, need_exact);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int xs = __shfl_sync(0xffffffffu, start, src), xe = __shfl_sync(0xffffffffu, end, src), xp = __shfl_sync(0xffffffffu, ptc, src);
+        const float x = __shfl_sync(0xffffffffu, qx, src), y = __shfl_sync(0xffffffffu, qy, src), z = __shfl_sync(0xffffffffu, qz, src);
+        knn_exact_warp<NS>(xs, xe, x, y, z, xyz, idx + (size_t)xp * NS, dist2 + (size_t)xp * NS, s_exact[threadIdx.x >> 5]);
+    }
 }
 
 }  // namespace
