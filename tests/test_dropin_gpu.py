@@ -206,3 +206,42 @@ def test_tensors_on_another_device_than_the_current_one(cuda):
         assert got.device.index == 1 and (got.cpu() == ref.cpu()).all()
     idx = epn_grouping.furthest_point_sampling(x, 64)
     assert idx.shape == (1, 64)
+
+
+def test_fit_smpl_loads_the_body_model_from_the_reference_paths(cuda, tmp_path, monkeypatch):
+    """fit_smpl without args.smpl_model reads datafolder/body_models/smpl/<gender>/SMPL_*.pkl relative to the working directory,
+    exactly where the reference looks (fit_SMPL.py:92-99); here the pickle is a synthetic SMPL-shaped model written in the SMPL
+    pickle layout (v_template, shapedirs, posedirs [V,3,207], J_regressor, kintree_table, weights, f)."""
+    import pickle
+    import types
+    import numpy as np
+    import torch
+    from etch_b200 import smpl_model
+    from etch_b200.models import fit_SMPL
+    body = smpl_model.synthetic_body(0)
+    V = body["v_template"].shape[0]
+    kin = np.stack([np.where(body["parents"] < 0, 2 ** 32 - 1, body["parents"]).astype(np.int64), np.arange(24)], 0)
+    pkl = {"v_template": body["v_template"].astype(np.float64), "shapedirs": body["shapedirs"].astype(np.float64),
+           "posedirs": body["posedirs"].T.reshape(V, 3, 207).astype(np.float64), "J_regressor": body["J_regressor"].astype(np.float64),
+           "kintree_table": kin, "weights": body["lbs_weights"].astype(np.float64), "f": body["faces"].astype(np.uint32)}
+    for rel in ("neutral/SMPL_NEUTRAL_10pc_rmchumpy.pkl", "male/SMPL_MALE_10pc.pkl"):
+        path = tmp_path / "datafolder" / "body_models" / "smpl" / rel
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with open(path, "wb") as fh:
+            pickle.dump(pkl, fh)
+    monkeypatch.chdir(tmp_path)
+    ms = json.load(open(os.path.join(ROOT, "etch_b200", "data", "superset_smpl.json")))
+    rng = np.random.default_rng(0)
+    N = 2000
+    inner = torch.from_numpy(body["v_template"][rng.integers(0, V, N)][None].astype(np.float32)).to(cuda)
+    labels = torch.from_numpy(rng.integers(0, 86, (1, N))).to(cuda)
+    conf = torch.from_numpy((0.4 + 0.5 * rng.random((1, N, 1))).astype(np.float32)).to(cuda)
+    a_file = types.SimpleNamespace(markerset=ms, device="cuda:0")
+    a_dict = types.SimpleNamespace(markerset=ms, device="cuda:0", smpl_model=body)
+    for gender in ("neutral", "male"):
+        m1, p1, v1, i1 = fit_SMPL.fit_smpl(a_file, inner, labels, conf, gender)
+        m2, p2, v2, i2 = fit_SMPL.fit_smpl(a_dict, inner, labels, conf, gender)
+        assert np.abs(np.asarray(m1[0].vertices) - np.asarray(m2[0].vertices)).max() < 1e-6
+        assert (np.asarray(m1[0].faces) == body["faces"]).all()
+    with pytest.raises(FileNotFoundError):
+        fit_SMPL.fit_smpl(a_file, inner, labels, conf, "female")      # no such file under the reference's path
