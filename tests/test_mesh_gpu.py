@@ -154,3 +154,25 @@ def test_oracle_closest_point_is_the_true_minimum():
     dd, ii = O.nearest_point(ref, pts)
     sd, si = cKDTree(ref).query(pts, k=1)
     assert (ii == si).all() and np.allclose(dd, sd, rtol=0, atol=1e-15)
+
+
+@pytest.mark.gpu
+def test_results_to_host_is_one_packed_copy_of_the_same_values(cuda):
+    """etch_b200.io.results_to_host (the per-batch D2H eval.py needs before its writers) returns exactly the device values."""
+    import json
+    import types
+    from etch_b200 import io, smpl_model, synth
+    from etch_b200.models.models_pointcloud import GT_network_equiv
+    from etch_b200.runtime import ScanFitter
+    ms = json.load(open(os.path.join(ROOT, "etch_b200", "data", "superset_smpl.json")))
+    net = GT_network_equiv(types.SimpleNamespace(output_folder=None, EPN_input_radius=0.4, EPN_layer_num=2, markerset=ms))
+    net.load_state_dict(synth.make_state_dict(1))
+    net = net.to(cuda).eval()
+    args = types.SimpleNamespace(markerset=ms, smpl_model=smpl_model.synthetic_body(0), device="cuda:0")
+    fit = ScanFitter(net, args, use_graph=False)(torch.from_numpy(synth.sample_real_scans(2, 1024, 4)).to(cuda))
+    host = io.results_to_host(fit)
+    for k in ("vertices", "joints", "params", "tightness", "inner", "markers", "confidences"):
+        np.testing.assert_array_equal(host[k], fit[k].cpu().numpy())
+    np.testing.assert_array_equal(host["labels"], fit["labels"].cpu().numpy())
+    np.testing.assert_array_equal(host["valid"], fit["valid"].cpu().numpy())
+    assert host["labels"].dtype == np.int64 and host["valid"].dtype == bool
