@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libetch_b200.so")
+_SO = os.environ.get("ETCH_B200_LIB") or os.path.join(_HERE, "libetch_b200.so")   # override: A/B builds of the same ABI (tools/)
 _lib = None
 
 

@@ -29,7 +29,10 @@ constexpr int NA = 60;
 constexpr int NK = 24;
 constexpr int NPAIRS = NA * NK;              // 1440 (anchor, kernel point) pairs
 constexpr int V3_JJ = 1;                     // neighbours per FMA-loop iteration (see the loop: unrolling costs ~60 MOVs per chunk)
-constexpr unsigned V3_SLEEP = 256;           // ns the idle control warp sleeps between polls
+#ifndef ETCH_V3_SLEEP_NS
+#define ETCH_V3_SLEEP_NS 256
+#endif
+constexpr unsigned V3_SLEEP = ETCH_V3_SLEEP_NS;  // ns the idle control warp sleeps between polls (A/B: tools/v3_sleep_ab.sh; 64 / 128 / 512 measured equal)
 constexpr int NBR_SLOT = 8192;               // one neighbour tile: 60 rows x 128 B, padded to the 1 KB swizzle atom
 constexpr int NBR_TX = NA * 128;             // bytes one TMA box delivers
 constexpr int CT = 480;                      // compute threads (15 warps)
