@@ -124,15 +124,17 @@ def _oracle_pipeline(pts, sd, body, ms):
     return out, labels, vec, inner, mk, valid, fit
 
 
-def test_points_to_vertices_matches_oracle(cuda):
-    """The whole hot path on 2 scans x 5000 points (one real-scan cloud, one synthetic-clothed body cloud):
+@pytest.mark.parametrize("B,N", [(2, 5000), (1, 10000)])
+def test_points_to_vertices_matches_oracle(cuda, B, N):
+    """The whole hot path on 2 scans x 5000 points (one real-scan cloud, one synthetic-clothed body cloud; BASELINE configs[1]) and on
+    one 10000-point scan (configs[2], "V2V/MPJPE checked vs reference"):
     GPU net -> GPU markers -> GPU LM fit  vs  oracle net -> oracle markers -> oracle LM fit, full 30+50 iterations."""
     from etch_b200 import smpl_model, synth
     from etch_b200.models import fit_SMPL
     ms = _markerset()
     net, sd = _model(cuda)
     body = smpl_model.synthetic_body(0)
-    pts = torch.from_numpy(synth.sample_real_scans(2, 5000, 3))
+    pts = torch.from_numpy(synth.sample_real_scans(B, N, 3))
     o_out, o_labels, o_vec, o_inner, o_mk, o_valid, o_fit = _oracle_pipeline(pts, sd, body, ms)
     d = pts.to(cuda)
     out, _ = net(d, ["confidence", "direction", "magnitude"], "standard_vector")
@@ -148,13 +150,14 @@ def test_points_to_vertices_matches_oracle(cuda):
     np.testing.assert_array_equal(valid.cpu().numpy(), o_valid.numpy())
     merr = np.linalg.norm(markers.cpu().numpy() - o_mk.numpy(), axis=-1)[o_valid.numpy()]
     _hist("marker |err| (m)", merr)
-    for b in range(2):
+    for b in range(B):
         v = np.asarray(meshes[b].vertices)
         v2v = 1000.0 * np.linalg.norm(v - o_fit["vertices"][b].numpy(), axis=-1).mean()
-        jerr = 1000.0 * np.linalg.norm(info[4][b] - o_fit["joints"][b].numpy(), axis=-1).max()
-        print("scan %d: V2V vs oracle %.4f mm, max joint err %.4f mm" % (b, v2v, jerr))
+        jd = 1000.0 * np.linalg.norm(info[4][b] - o_fit["joints"][b].numpy(), axis=-1)
+        jerr, mpjpe = jd.max(), jd[:22].mean()       # MPJPE over the first 22 joints (scripts/experiment_scripts/compute_mpjpe_error.py:23-24)
+        print("scan %d: V2V vs oracle %.4f mm, MPJPE(22) %.4f mm, max joint err %.4f mm" % (b, v2v, mpjpe, jerr))
         if np.isfinite(o_fit["vertices"][b].numpy()).all():
-            assert v2v <= 1.0 and jerr <= 1.0, (b, v2v, jerr)
+            assert v2v <= 1.0 and jerr <= 1.0 and mpjpe <= 1.0, (b, v2v, mpjpe, jerr)
         else:   # a NaN marker (conf**20 underflow) makes the reference's fit NaN as well
             assert not np.isfinite(v).all()
     assert np.quantile(merr, 0.9) <= 1e-4 and merr.max() <= 1e-3, (np.quantile(merr, 0.9), merr.max())
