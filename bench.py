@@ -165,7 +165,7 @@ def run_reference(args, rank, world):
     budget_s = float(os.environ.get("ETCH_REF_BUDGET_S", "900"))
     t_start = time.time()
     times, nets, lms = [], [], []
-    warm = min(args.warmup, 1)   # the CPU path has nothing to warm beyond the first torch.func trace
+    warm = args.warmup           # honoured as given (one scan each), although the CPU path has nothing to warm beyond the first trace
     for i in range(warm + args.steps):
         pts = torch.from_numpy(synth.sample_real_scans(1, args.points, 100 + i))
         dt, t_net, t_lm, _ = _oracle_scan(pts, sd, tables, body_t, vids, len(ms))
