@@ -220,7 +220,9 @@ class Pipeline:
         self.net = self.net.to(device).eval()
         self.args = types.SimpleNamespace(markerset=self.ms, smpl_model=smpl_model.synthetic_body(0), device=str(device))
         self.device = device
-        self.fitter = ScanFitter(self.net, self.args, "neutral", use_graph=use_graph, in_flight=in_flight)
+        # ETCH_SM_BUDGET: experiment knob -- SMs the persistent kernels fill (default: SM count - scans per batch when batches overlap)
+        budget = int(os.environ["ETCH_SM_BUDGET"]) if os.environ.get("ETCH_SM_BUDGET") else None
+        self.fitter = ScanFitter(self.net, self.args, "neutral", use_graph=use_graph, in_flight=in_flight, sm_budget=budget)
         self.eager = ScanFitter(self.net, self.args, "neutral", use_graph=False)
 
     def step(self, pts):
@@ -266,8 +268,6 @@ def run_etch(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl etch needs a CUDA device (there is no CPU fallback); use gpurun")
     build.build()
-    if os.environ.get("ETCH_SM_BUDGET"):     # experiment knob: SMs the persistent kernels fill (default: all 148)
-        _lib.lib().etch_set_sm_budget(int(os.environ["ETCH_SM_BUDGET"]))
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:

@@ -41,12 +41,13 @@ class _Slot:
 
 class ScanFitter:
     def __init__(self, net, args, gender="neutral", use_graph=True, scale_magnitude=10.0,
-                 steps_stage0=30, steps_stage1=50, lr_stage0=0.5, lr_stage1=0.2, in_flight=1):
+                 steps_stage0=30, steps_stage1=50, lr_stage0=0.5, lr_stage1=0.2, in_flight=1, sm_budget=None):
         self.net, self.args, self.gender = net, args, gender
         self.use_graph = use_graph
         self.in_flight = max(1, int(in_flight)) if use_graph else 1
         self.scale = scale_magnitude
         self.lm = dict(steps_stage0=steps_stage0, steps_stage1=steps_stage1, lr_stage0=lr_stage0, lr_stage1=lr_stage1)
+        self.sm_budget = sm_budget   # SMs the persistent kernels fill; None = SM count - scans per batch when batches overlap
         self._slots = {}     # (shape, device index) -> [ _Slot ] * in_flight
         self._next = {}
         self.launches_per_step = None
@@ -76,7 +77,7 @@ class ScanFitter:
             # leave one SM per scan to the one-CTA-per-scan kernels (FPS, LM fit) of the other batches in flight: the persistent
             # full-grid kernels then never wait for an SM one of those holds for milliseconds (+2 % scans/s at 8 batches in flight)
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            _lib.lib().etch_set_sm_budget(max(sms // 2, sms - int(example.shape[0])))
+            _lib.lib().etch_set_sm_budget(int(self.sm_budget) if self.sm_budget else max(sms // 2, sms - int(example.shape[0])))
         slots = []
         for _ in range(self.in_flight):
             sl = _Slot()
