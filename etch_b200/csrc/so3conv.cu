@@ -42,8 +42,13 @@ __device__ __forceinline__ void stats_to_affine(const double* sums, int b, int C
 
 // ------------------------------------------------------------------------------------------------
 // Layer b0.0: c_in = 1 and the input feature is identically 1  =>  y[a,k] = sum_n w[a,k,n];  z = W y + bias.
+// 480 threads: thread t owns the (anchor, kernel point) pairs t, t + 480, t + 960 for every point it sees, so their rotated kernel
+// points stay in registers ({2/sigma R_a k, |R_a k|^2/sigma}: the expanded form of the weight that the c_in > 1 kernel uses too,
+// w = relu(g . kq.xyz + (1 - |g|^2/sigma) - kq.w): 3 FFMA + FADD + FMNMX per (pair, neighbour) instead of 12 instructions) and one
+// broadcast LDS.128 per neighbour feeds three pairs.
+constexpr int C1_THREADS = 480;
 template <int COUT>
-__global__ void __launch_bounds__(256) inter_conv_c1_kernel(
+__global__ void __launch_bounds__(C1_THREADS) inter_conv_c1_kernel(
     const float* __restrict__ xyz,       // [B,3,q] support points
     const int* __restrict__ sample_idx,  // [B,P]   centres (indices into q)
     const int* __restrict__ nbr,         // [B,P,nn]
@@ -54,16 +59,22 @@ __global__ void __launch_bounds__(256) inter_conv_c1_kernel(
     float* __restrict__ zraw,            // [B,P,60,COUT]
     double* __restrict__ stats)          // [B][COUT][2]
 {
-    __shared__ float s_kr[NA * NK * 3];
-    __shared__ float s_W[NK * COUT];
-    __shared__ float s_bias[COUT];
-    __shared__ float s_g[64 * 3];
+    static_assert(NA * NK == 3 * C1_THREADS, "three pairs per thread");
+    __shared__ __align__(16) float s_W[NK * COUT];
+    __shared__ __align__(16) float s_bias[COUT];
+    __shared__ float4 s_g[64];
     __shared__ float s_y[NA * NK];
-    __shared__ float s_z[NA * COUT];
+    __shared__ __align__(16) float s_z[NA * COUT];
     const int b = blockIdx.y, tid = threadIdx.x;
-    for (int i = tid; i < NA * NK * 3; i += 256) s_kr[i] = __ldg(kr + i);
-    for (int i = tid; i < NK * COUT; i += 256) s_W[i] = __ldg(Wt + i);
+    for (int i = tid; i < NK * COUT; i += C1_THREADS) s_W[i] = __ldg(Wt + i);
     if (tid < COUT) s_bias[tid] = __ldg(bias + tid);
+    float4 kq[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int t = tid + u * C1_THREADS;
+        const float kx = __ldg(kr + t * 3), ky = __ldg(kr + t * 3 + 1), kz = __ldg(kr + t * 3 + 2);
+        kq[u] = make_float4(2.0f * inv_sigma * kx, 2.0f * inv_sigma * ky, 2.0f * inv_sigma * kz, (kx * kx + ky * ky + kz * kz) * inv_sigma);
+    }
     const float* X = xyz + (size_t)b * 3 * q;
     double acc_s = 0.0, acc_ss = 0.0;
     for (int p = blockIdx.x; p < P; p += gridDim.x) {
@@ -71,29 +82,33 @@ __global__ void __launch_bounds__(256) inter_conv_c1_kernel(
         if (tid < nn) {
             const int c = __ldg(sample_idx + (size_t)b * P + p);
             const int k = __ldg(nbr + ((size_t)b * P + p) * nn + tid);
-            s_g[tid * 3 + 0] = __ldg(X + k) - __ldg(X + c);
-            s_g[tid * 3 + 1] = __ldg(X + q + k) - __ldg(X + q + c);
-            s_g[tid * 3 + 2] = __ldg(X + 2 * (size_t)q + k) - __ldg(X + 2 * (size_t)q + c);
+            const float gx = __ldg(X + k) - __ldg(X + c), gy = __ldg(X + q + k) - __ldg(X + q + c);
+            const float gz = __ldg(X + 2 * (size_t)q + k) - __ldg(X + 2 * (size_t)q + c);
+            s_g[tid] = make_float4(gx, gy, gz, 1.0f - (gx * gx + gy * gy + gz * gz) * inv_sigma);
         }
         __syncthreads();
-        for (int t = tid; t < NA * NK; t += 256) {
-            const float kx = s_kr[t * 3], ky = s_kr[t * 3 + 1], kz = s_kr[t * 3 + 2];
-            float s = 0.f;
-            for (int n = 0; n < nn; ++n) {
-                const float dx = s_g[n * 3] - kx, dy = s_g[n * 3 + 1] - ky, dz = s_g[n * 3 + 2] - kz;
-                const float d = dx * dx + dy * dy + dz * dz;
-                s += fmaxf(1.0f - d * inv_sigma, 0.f);
-            }
-            s_y[t] = s;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int n = 0; n < nn; ++n) {
+            const float4 g = s_g[n];
+            s0 += fmaxf(fmaf(g.x, kq[0].x, fmaf(g.y, kq[0].y, fmaf(g.z, kq[0].z, g.w - kq[0].w))), 0.f);
+            s1 += fmaxf(fmaf(g.x, kq[1].x, fmaf(g.y, kq[1].y, fmaf(g.z, kq[1].z, g.w - kq[1].w))), 0.f);
+            s2 += fmaxf(fmaf(g.x, kq[2].x, fmaf(g.y, kq[2].y, fmaf(g.z, kq[2].z, g.w - kq[2].w))), 0.f);
         }
+        s_y[tid] = s0; s_y[tid + C1_THREADS] = s1; s_y[tid + 2 * C1_THREADS] = s2;
         __syncthreads();
-        for (int t = tid; t < NA * COUT; t += 256) {
-            const int a = t / COUT, o = t % COUT;
-            float z = s_bias[o];
+        // channel mixing 24 -> COUT: thread (anchor, 4 consecutive output channels): one scalar y and one LDS.128 of W per 4 FMAs
+        for (int t = tid; t < NA * (COUT / 4); t += C1_THREADS) {
+            const int a = t / (COUT / 4), o4 = (t % (COUT / 4)) * 4;
+            float4 z = *reinterpret_cast<const float4*>(s_bias + o4);
 #pragma unroll
-            for (int k = 0; k < NK; ++k) z = fmaf(s_W[k * COUT + o], s_y[a * NK + k], z);
-            s_z[t] = z;
-            zraw[((size_t)b * P + p) * NA * COUT + t] = z;
+            for (int k = 0; k < NK; ++k) {
+                const float y = s_y[a * NK + k];
+                const float4 w = *reinterpret_cast<const float4*>(s_W + k * COUT + o4);
+                z.x = fmaf(w.x, y, z.x); z.y = fmaf(w.y, y, z.y); z.z = fmaf(w.z, y, z.z); z.w = fmaf(w.w, y, z.w);
+            }
+            *reinterpret_cast<float4*>(s_z + a * COUT + o4) = z;
+            *reinterpret_cast<float4*>(zraw + ((size_t)b * P + p) * NA * COUT + a * COUT + o4) = z;
         }
         __syncthreads();
         if (tid < COUT) {
@@ -416,8 +431,8 @@ ETCH_API int etch_so3_inter_conv_c1(const float* xyz, const int* sample_idx, con
     if (!xyz || !sample_idx || !nbr || !kr || !Wt || !bias || !zraw || !stats || nn > 64 || nn <= 0) return ETCH_EINVAL;
     const float inv_sigma = 1.0f / sigma;
     dim3 grid(min(P, 148 * 8), B);
-    if (cout == 32) inter_conv_c1_kernel<32><<<grid, 256, 0, stream>>>(xyz, sample_idx, nbr, kr, Wt, bias, q, P, nn, inv_sigma, zraw, stats);
-    else if (cout == 64) inter_conv_c1_kernel<64><<<grid, 256, 0, stream>>>(xyz, sample_idx, nbr, kr, Wt, bias, q, P, nn, inv_sigma, zraw, stats);
+    if (cout == 32) inter_conv_c1_kernel<32><<<grid, C1_THREADS, 0, stream>>>(xyz, sample_idx, nbr, kr, Wt, bias, q, P, nn, inv_sigma, zraw, stats);
+    else if (cout == 64) inter_conv_c1_kernel<64><<<grid, C1_THREADS, 0, stream>>>(xyz, sample_idx, nbr, kr, Wt, bias, q, P, nn, inv_sigma, zraw, stats);
     else return ETCH_EINVAL;
     ETCH_RETURN_LAST();
 }
