@@ -626,6 +626,34 @@ struct BodyFull {
 };
 
 // params [B][85] = theta(72: orient, pose) | beta(10) | transl(3)  ->  verts [B][V][3], joints [B][45][3]
+// Test hook (include/etch_b200_probes.h): residual and analytic Jacobian of the marker cost at GIVEN parameters, written out so that
+// tests/test_fit_gpu.py can compare them with the autodiff Jacobian of the oracle.  One CTA per scan;
+// res [B][3M], jac [B][3M][85] with columns theta(72: orient | pose) | beta(10) | transl(3).
+__global__ void __launch_bounds__(256, 1) lm_jacobian_dump_kernel(const float* __restrict__ params, const float* __restrict__ markers,
+                                                                  const unsigned char* __restrict__ valid, BodyMarkers Bm,
+                                                                  float* __restrict__ res, float* __restrict__ jac) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LmSmem& S = *reinterpret_cast<LmSmem*>(smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x, M = Bm.M;
+    for (int i = tid; i < DMAX + 3; i += blockDim.x) S.x[i] = i < DMAX ? __ldg(params + (size_t)b * DMAX + i) : 0.f;
+    for (int i = tid; i < M * 3; i += blockDim.x) S.tgt[i] = __ldg(markers + (size_t)b * M * 3 + i);
+    for (int i = tid; i < M; i += blockDim.x) S.mask[i] = valid[(size_t)b * M + i] ? 1.f : 0.f;
+    for (int m = tid; m < M; m += blockDim.x) {
+        int cnt = 0;
+        for (int k = 0; k < NJ; ++k) {
+            const float w = __ldg(Bm.Wm + m * NJ + k);
+            if (w != 0.f) { S.Wm[m * NJ + cnt] = w; S.nzk[m * NJ + cnt] = (unsigned char)k; ++cnt; }
+        }
+        S.nzc[m] = cnt;
+    }
+    for (int i = tid; i < NJ; i += blockDim.x) S.anc[i] = __ldg(Bm.ancmask + i);
+    __syncthreads();
+    lm_eval(S, Bm);
+    lm_jacobian(S, Bm, 10);
+    for (int i = tid; i < M * 3; i += blockDim.x) res[(size_t)b * M * 3 + i] = S.res[i];
+    for (int i = tid; i < M * 3 * DMAX; i += blockDim.x) jac[(size_t)b * M * 3 * DMAX + i] = S.J[(i / DMAX) * LDJ + i % DMAX];
+}
+
 __global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ params, BodyFull Bf, float* __restrict__ verts,
                                                   float* __restrict__ joints) {
     __shared__ float sR[NJ * 9], sG[NJ * 12], sA[NJ * 12], sJ[NJ * 3], spf[207], sx[DMAX];
@@ -742,6 +770,17 @@ ETCH_API int etch_lm_fit_profile(const float* markers, const unsigned char* vali
 }
 
 // SMPL forward for the fitted parameters (fit_SMPL.py:257-258): verts [B,V,3], joints [B,45,3] (translation applied)
+ETCH_API int etch_lm_jacobian_dump(const float* params, const float* markers, const unsigned char* valid, const float* Tm, const float* Sm,
+                                   const float* Pm, const float* Wm, const float* Jt, const float* Js, const int* parents,
+                                   const unsigned* ancmask, int B, int M, float* res, float* jac, cudaStream_t stream) {
+    if (!params || !markers || !valid || !Tm || !Sm || !Pm || !Wm || !Jt || !Js || !parents || !ancmask || !res || !jac || B <= 0 || M <= 0 || M > NM_MAX)
+        return ETCH_EINVAL;
+    BodyMarkers Bm{Tm, Sm, Pm, Wm, Jt, Js, parents, ancmask, M};
+    ETCH_TRY(cudaFuncSetAttribute(lm_jacobian_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem)));
+    lm_jacobian_dump_kernel<<<B, 256, sizeof(LmSmem), stream>>>(params, markers, valid, Bm, res, jac);
+    ETCH_RETURN_LAST();
+}
+
 ETCH_API int etch_lbs_forward(const float* params, const float* v_template, const float* shapedirs, const float* posedirs,
                               const float* weights, const float* Jt, const float* Js, const int* parents,
                               const int* extra_vids, int B, int V, float* verts, float* joints, cudaStream_t stream) {

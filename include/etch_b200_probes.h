@@ -30,6 +30,12 @@ int etch_ffma_rate(long long* out, int ctas, int warps, int iters, int mode, cud
  * cost of the M = c_in mapping of the InterSO3Conv neighbour contraction that DESIGN.md argues against (mode 1: M = 128; mode 2: N = 128 + 64) */
 int etch_umma_contract_probe(long long* out, int ctas, int steps, int ring, int mode, cudaStream_t stream);
 
+/* test hook: residual res [B,3M] and analytic Jacobian jac [B,3M,85] (columns orient 3 | pose 69 | betas 10 | transl 3) of the marker cost that
+ * etch_lm_fit minimises, at the given packed parameters [B,85] (tests/test_fit_gpu.py compares them with the oracle's autodiff Jacobian) */
+int etch_lm_jacobian_dump(const float* params, const float* markers, const unsigned char* valid, const float* Tm, const float* Sm,
+                          const float* Pm, const float* Wm, const float* Jt, const float* Js, const int* parents,
+                          const unsigned* ancmask, int B, int M, float* res, float* jac, cudaStream_t stream);
+
 /* probe: reads and resets the diagnostic counters of etch_knn_grid (HOST pointer to 2 values: fallback queries, candidates visited); the
  * counters only tick in a library built with -DETCH_KNN_STATS */
 int etch_knn_grid_stats(unsigned long long* out_host);

@@ -126,3 +126,42 @@ def test_fit_smpl_contract(cuda):
     assert [a.shape for a in info] == [(B, 23, 3), (B, 10), (B, 3), (B, 3), (B, 45, 3)]
     with pytest.raises(ValueError):
         fit_smpl(args, inner.to(cuda), labels.to(cuda), conf.to(cuda), "robot")
+
+
+def test_analytic_jacobian_matches_autodiff(cuda):
+    """the closed-form marker-only Jacobian inside etch_lm_fit against torch.func.jacrev through the
+    oracle's full-mesh LBS (what theseus' AutoDiffCostFunction differentiates, fit_SMPL.py:111-152,179,230), at random poses / shapes,
+    at the zero pose the solve starts from (Rodrigues singularity) and with some markers masked out."""
+    from etch_b200 import _lib as L, smpl_model
+    from etch_b200.models import fit_SMPL as F
+    from oracle import lm as olm
+    body = smpl_model.synthetic_body(0)
+    model, vids, target, mask, _ = _synthetic_targets(body, 3, 5)
+    mask = mask.clone()
+    mask[1, ::7] = False
+    g = torch.Generator().manual_seed(3)
+    B, M = 3, target.shape[1]
+    params = torch.zeros(B, 85)
+    params[1:, 0:72] = 0.4 * torch.randn(2, 72, generator=g)        # orient | pose   (row 0 stays at the zero pose)
+    params[1:, 72:82] = torch.randn(2, 10, generator=g)             # betas
+    params[:, 82:85] = 0.2 * torch.randn(B, 3, generator=g)         # transl
+    T = F.body_tables(_args(body), "neutral", cuda)
+    res = torch.empty(B, M * 3, device=cuda)
+    jac = torch.empty(B, M * 3, 85, device=cuda)
+    dp, dt, dm = params.to(cuda), target.to(cuda).contiguous(), mask.to(torch.uint8).to(cuda).contiguous()
+    L.call("lm_jacobian_dump", L.ptr(dp), L.ptr(dt), L.ptr(dm), L.ptr(T.Tm), L.ptr(T.Sm), L.ptr(T.Pm), L.ptr(T.Wm), L.ptr(T.Jt), L.ptr(T.Js),
+           L.ptr(T.parents), L.ptr(T.ancmask), B, M, L.ptr(res), L.ptr(jac))
+    torch.cuda.synchronize()
+    vid_t = torch.as_tensor(vids, dtype=torch.long)
+    for b in range(B):
+        # oracle variable order: pose 69 | betas 10 | orient 3 | transl 3   ->   kernel column order: orient 3 | pose 69 | betas 10 | transl 3
+        x = torch.cat([params[b, 3:72], params[b, 72:82], params[b, 0:3], params[b, 82:85]])
+        f = lambda xi: olm._residual(xi, 10, model, vid_t, target[b], mask[b].float())      # noqa: E731
+        r_ref = f(x)
+        J_ref = torch.func.jacrev(f)(x)
+        J_ref = torch.cat([J_ref[:, 79:82], J_ref[:, 0:69], J_ref[:, 69:79], J_ref[:, 82:85]], 1)
+        r_err = (res[b].cpu() - r_ref).abs().max().item()
+        J_err = (jac[b].cpu() - J_ref).abs().max().item()
+        print("scan %d: residual max err %.2e, Jacobian max err %.2e (|J| max %.2f)" % (b, r_err, J_err, J_ref.abs().max().item()))
+        assert r_err < 2e-6 and J_err < 2e-4 * max(1.0, J_ref.abs().max().item())
+    assert (jac[1].cpu().view(M, 3, 85)[::7] == 0).all()            # masked markers contribute nothing
