@@ -163,5 +163,5 @@ def test_analytic_jacobian_matches_autodiff(cuda):
         r_err = (res[b].cpu() - r_ref).abs().max().item()
         J_err = (jac[b].cpu() - J_ref).abs().max().item()
         print("scan %d: residual max err %.2e, Jacobian max err %.2e (|J| max %.2f)" % (b, r_err, J_err, J_ref.abs().max().item()))
-        assert r_err < 2e-6 and J_err < 2e-4 * max(1.0, J_ref.abs().max().item())
+        assert r_err < 2e-6 and J_err < 5e-6 * max(1.0, J_ref.abs().max().item())      # measured on B200: 4.8e-7
     assert (jac[1].cpu().view(M, 3, 85)[::7] == 0).all()            # masked markers contribute nothing
