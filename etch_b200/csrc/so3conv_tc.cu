@@ -123,16 +123,33 @@ __global__ void __launch_bounds__(288, (AgemmCfg<CIN, COUT, J>::CTAS_PER_SM)) an
         const bool fok = frow < NPAIR;
         const int fpl = fok ? frow / NA : 0, fa = fok ? frow % NA : 0;
         uint32_t g = 0, ntile_done = 0;
+        // The tile's activations are fetched one tile ahead into registers: the global / L2 latency of the staging loads (17 % of the
+        // kernel's warp time in the round-1 profile, more for the single-slot skip conv) hides behind the fills of the previous tile.
+        constexpr int NV = (NPAIR * (CIN / 4) + 255) / 256;
+        float4 pre[NV];
+        auto fetch_tile = [&](int tile_) {
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int t = tid + u * 256;
+                if (t < NPAIR * (CIN / 4)) {
+                    const int row = t / (CIN / 4), c4 = t % (CIN / 4);
+                    const int p = min(tile_ * TP + row / NA, P - 1);
+                    const int sp = src_idx ? __ldg(src_idx + (size_t)b * P + p) : p;
+                    pre[u] = __ldg(reinterpret_cast<const float4*>(xin + (((size_t)b * Q + sp) * NA + (row % NA)) * CIN) + c4);
+                }
+            }
+        };
+        if ((int)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int p0 = tile * TP;
             const int npts = min(TP, P - p0);
             // stage (and normalise) the activations of the tile's points
-            for (int t = tid; t < NPAIR * (CIN / 4); t += 256) {
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                const int t = tid + u * 256;
+                if (t >= NPAIR * (CIN / 4)) break;
                 const int row = t / (CIN / 4), c4 = t % (CIN / 4);
-                const int pl = row / NA;
-                const int p = min(p0 + pl, P - 1);
-                const int sp = src_idx ? __ldg(src_idx + (size_t)b * P + p) : p;
-                float4 v = __ldg(reinterpret_cast<const float4*>(xin + (((size_t)b * Q + sp) * NA + (row % NA)) * CIN) + c4);
+                float4 v = pre[u];
                 if (NORM_IN) {
                     const int c = c4 * 4;
                     v.x = etch_lrelu((v.x - s_mean[c]) * s_rstd[c]);
@@ -143,6 +160,7 @@ __global__ void __launch_bounds__(288, (AgemmCfg<CIN, COUT, J>::CTAS_PER_SM)) an
                 *reinterpret_cast<float4*>(s_x + row * LD + c4 * 4) = v;
             }
             compute_warps_sync();
+            if (tile + (int)gridDim.x < ntiles) fetch_tile(tile + gridDim.x);
 
             for (int j = 0; j < J; ++j, ++g) {
                 const uint32_t ab = g & 1;
