@@ -283,8 +283,8 @@ __device__ __forceinline__ float dh_ex2(float x) {
 }
 
 // softmax(q K^T) V for (token = my TMEM lane, my 4 heads); output written as (hi, lo) into the canonical O tile.
-// Online softmax over 3 chunks of 20 keys keeps the unrolled body small (the fully unrolled 4 x 60-key version
-// thrashed the instruction cache: stall_no_inst dominated the profile) at the cost of 3 extra exp's per head.
+// Online softmax over 2 chunks of 30 keys (round 2 A/B: 5.15 ms vs 5.23 ms with 3 chunks of 20) keeps the unrolled body small (the fully unrolled 4 x 60-key version
+// thrashed the instruction cache: stall_no_inst dominated the profile) at the cost of 2 extra exp's per head.
 __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, unsigned char* s_O, int warp, int lane) {
     const int q = warp & 3, hq = (warp >> 2) * 4;
     const int row = q * 32 + lane;
@@ -300,11 +300,11 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
         float mx = -INFINITY, sum = 0.f;
         float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-        for (int j0 = 0; j0 < DH_NA; j0 += 20) {
-            float s[20];
+        for (int j0 = 0; j0 < DH_NA; j0 += 30) {
+            float s[30];
             float cm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 20; ++j) {
+            for (int j = 0; j < 30; ++j) {
                 const float* kr = s_kv + (base + j0 + j) * DH_LDKV + h * 8;
                 const float4 ka = *reinterpret_cast<const float4*>(kr);
                 const float4 kb = *reinterpret_cast<const float4*>(kr + 4);
@@ -321,7 +321,7 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
 #pragma unroll
             for (int d = 0; d < 8; ++d) o[d] *= sc;
 #pragma unroll
-            for (int j = 0; j < 20; ++j) {
+            for (int j = 0; j < 30; ++j) {
                 const float p = dh_ex2(s[j] - mn);
                 sum += p;
                 const float* vr = s_kv + (base + j0 + j) * DH_LDKV + 64 + h * 8;
