@@ -173,7 +173,9 @@ ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float*
 //                                      from TMEM, the hidden layer is never stored)
 // Activations live in shared memory as (hi, lo) TF32 pairs in the canonical UMMA layout (x == hi + lo exactly), weights
 // stream as 18 pre-split [64 rows x 32 k] slices per tile through a 2-deep cp.async.bulk ring.  The softmax attention itself is
-// block-diagonal (60x60 per point and head) and stays on the CUDA cores.
+// block-diagonal (60x60 per point and head) and stays on the CUDA cores.  Two overlaps inside a tile: the K and V blocks of a QKV
+// projection are issued before the Q block, so K|V move to shared memory under the Q MMAs, and the NEXT tile's tokens are blended
+// into X (dead once the layer-2 QKV MMAs have completed) while the last two MMA blocks of the current tile run.
 namespace {
 
 constexpr int DH_NA = 60;
@@ -241,7 +243,9 @@ struct DhIssuer {   // state of the weight-streaming / MMA-issuing warp (all fie
         if (ld >= DH_NCHUNK) return;
         const uint32_t buf = gl & 1;
         if (gl >= 2) umma::mbar_wait(&b_empty[buf], ((gl - 2) >> 1) & 1);
-        umma::bulk_load(s_B + buf * 2 * DH_WB, wall + (size_t)ld * 2 * 64 * 32, 2 * DH_WB, &b_full[buf]);
+        // streaming order: K and V blocks before the Q block of a QKV phase (K|V are copied to shared memory under the Q MMAs)
+        const int sl = ld < 6 ? (ld < 4 ? ld + 2 : ld - 4) : (ld >= 8 && ld < 14 ? (ld < 12 ? ld + 2 : ld - 4) : ld);
+        umma::bulk_load(s_B + buf * 2 * DH_WB, wall + (size_t)sl * 2 * 64 * 32, 2 * DH_WB, &b_full[buf]);
         ++ld; ++gl;
     }
     // one 64-column block of the output = two slices (K halves 0..31, 32..63) accumulated into tmem_d[0:64]
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     float* s_w = s_part + 256;                             // [128]
     float* s_anc = s_w + 128;                              // [60][9]
     __shared__ __align__(16) float s_bc1[64], s_bf[128], s_vreg[128];
-    __shared__ uint64_t b_full[2], b_empty[2], bar_mma;
+    __shared__ uint64_t b_full[2], b_empty[2], bar_mma, bar_kv;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < DH_NA * 9; i += 256) s_anc[i] = __ldg(anchors + i);
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     if (tid == 0) {
         umma::mbar_init(&b_full[0], 1); umma::mbar_init(&b_full[1], 1);
         umma::mbar_init(&b_empty[0], 1); umma::mbar_init(&b_empty[1], 1);
-        umma::mbar_init(&bar_mma, 1);
+        umma::mbar_init(&bar_mma, 1); umma::mbar_init(&bar_kv, 1);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -383,17 +387,14 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     const uint32_t tmem = umma::uniform(tmem_base);
     const uint32_t x_hi = umma::smem_u32(s_X), x_lo = x_hi + DH_XB, o_hi = umma::smem_u32(s_O), o_lo = o_hi + DH_XB;
     DhIssuer iss{wall, s_B, b_full, b_empty, 0u, 0u, 0};
-    uint32_t n_mma = 0;
+    uint32_t n_mma = 0, n_kv = 0;
     const int ntiles = (N + 1) / 2;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
 
-    // scan-major tile sequence: the whole grid blends from one scan's coarse features at a time (19 MB, L2 resident) instead of
-    // all B of them (the scan-parallel grid re-read them 4x from DRAM)
-    for (int gt = blockIdx.x; gt < ntiles * nscans; gt += gridDim.x) {
-        const int b = gt / ntiles, tile = gt - b * ntiles;
+    auto blend = [&](int g) {
+        const int b = g / ntiles, tile = g - b * ntiles;
         const float* F = feats + (size_t)b * S * DH_NA * 64;
         const int p0 = tile * 2;
-        if (warp == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
         // ---- 0. blend the three coarse rows into the token tile (hi/lo, canonical) ----
         {
             const int r = tid >> 1, hf = tid & 1;
@@ -427,18 +428,33 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
                 *reinterpret_cast<float4*>(s_X + DH_XB + kc * (128 * 16) + r * 16) = lo;
             }
         }
+    };
+
+    // scan-major tile sequence: the whole grid blends from one scan's coarse features at a time (19 MB, L2 resident) instead of
+    // all B of them (the scan-parallel grid re-read them 4x from DRAM)
+    for (int gt = blockIdx.x; gt < ntiles * nscans; gt += gridDim.x) {
+        const int b = gt / ntiles, tile = gt - b * ntiles;
+        const float* F = feats + (size_t)b * S * DH_NA * 64;
+        const int p0 = tile * 2;
+        if (warp == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
+        if (gt == (int)blockIdx.x) blend(gt);   // later tiles are blended under the previous tile's last MMAs
         for (int layer = 0; layer < 2; ++layer) {
             umma::fence_async_smem();
             __syncthreads();
             // ---- QKV projection: 6 slices -> D[0:192] ----
             if (warp == 0) {
                 umma::fence_after_sync();
-                for (int c = 0; c < 3; ++c) iss.mma_block(x_hi, x_lo, tmem + c * 64);
+                iss.mma_block(x_hi, x_lo, tmem + 64);
+                iss.mma_block(x_hi, x_lo, tmem + 128);
+                umma::commit(&bar_kv);
+                iss.mma_block(x_hi, x_lo, tmem);
                 umma::commit(&bar_mma);
             }
-            umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
+            umma::mbar_wait(&bar_kv, n_kv & 1); ++n_kv;
             umma::fence_after_sync();
             dh_store_kv(tmem, s_kv, warp, lane);
+            umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
+            umma::fence_after_sync();
             __syncthreads();
             dh_attention(tmem, s_kv, s_O, warp, lane);
             umma::fence_before_sync();
@@ -478,6 +494,8 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             for (int c = 0; c < 2; ++c) iss.mma_block(o_hi, o_lo, tmem + 256 + c * 64);
             umma::commit(&bar_mma);
         }
+        // X is dead since the layer-2 QKV MMAs completed: blend the next tile's tokens while the last MMAs run
+        if (gt + (int)gridDim.x < ntiles * nscans) blend(gt + gridDim.x);
         umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
         umma::fence_after_sync();
         {
