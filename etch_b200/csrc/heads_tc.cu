@@ -179,6 +179,7 @@ ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float*
 namespace {
 
 constexpr int DH_NA = 60;
+constexpr int DH_CHUNK = 60;                       // keys per online-softmax chunk (must divide 60)
 constexpr int DH_LDKV = 132;                       // floats per row of the K|V tile
 constexpr uint32_t DH_XB = 128 * 64 * 4;           // bytes of one canonical [128 x 64] tile
 constexpr uint32_t DH_WB = 64 * 32 * 4;            // bytes of one (hi or lo) weight slice [64 rows x 32 k]
@@ -286,9 +287,17 @@ __device__ __forceinline__ float dh_ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ uint64_t dh_pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void dh_unpk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t dh_fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t dh_mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // softmax(q K^T) V for (token = my TMEM lane, my 4 heads); output written as (hi, lo) into the canonical O tile.
-// Online softmax over 2 chunks of 30 keys (round 2 A/B: 5.15 ms vs 5.23 ms with 3 chunks of 20) keeps the unrolled body small (the fully unrolled 4 x 60-key version
-// thrashed the instruction cache: stall_no_inst dominated the profile) at the cost of 2 extra exp's per head.
+// Both products run as packed fma.rn.f32x2 (FFMA2: two lanes of the 8-wide head per instruction, the probability as a broadcast
+// operand): 17 instead of 24 issued instructions per key, the FP32 pipe time (16 lane-FMAs per key) is unchanged -- round 2 A/B
+// 5.09 -> 4.85 ms for the kernel.  The scores of a head are summed as (d0+d2+d4+d6) + (d1+d3+d5+d7).  Chunks of 20 / 30 / 60 keys
+// measure the same within noise (4.87 / 4.88 / 4.85 ms); one head's 60 keys are unrolled, the heads are not (the 4 x 60-key body of
+// the first version thrashed the instruction cache).
 __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, unsigned char* s_O, int warp, int lane) {
     const int q = warp & 3, hq = (warp >> 2) * 4;
     const int row = q * 32 + lane;
@@ -302,19 +311,22 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
 #pragma unroll
         for (int d = 0; d < 8; ++d) qv[d] *= 1.4426950408889634f;         // scores in log2 units: every exponential is one MUFU.EX2
         float mx = -INFINITY, sum = 0.f;
-        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint64_t q01 = dh_pk(qv[0], qv[1]), q23 = dh_pk(qv[2], qv[3]), q45 = dh_pk(qv[4], qv[5]), q67 = dh_pk(qv[6], qv[7]);
+        uint64_t o2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll 1
-        for (int j0 = 0; j0 < DH_NA; j0 += 30) {
-            float s[30];
+        for (int j0 = 0; j0 < DH_NA; j0 += DH_CHUNK) {
+            float s[DH_CHUNK];
             float cm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 30; ++j) {
+            for (int j = 0; j < DH_CHUNK; ++j) {
                 const float* kr = s_kv + (base + j0 + j) * DH_LDKV + h * 8;
-                const float4 ka = *reinterpret_cast<const float4*>(kr);
-                const float4 kb = *reinterpret_cast<const float4*>(kr + 4);
-                float v = qv[0] * ka.x;
-                v = fmaf(qv[1], ka.y, v); v = fmaf(qv[2], ka.z, v); v = fmaf(qv[3], ka.w, v);
-                v = fmaf(qv[4], kb.x, v); v = fmaf(qv[5], kb.y, v); v = fmaf(qv[6], kb.z, v); v = fmaf(qv[7], kb.w, v);
+                const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(kr);
+                const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(kr + 4);
+                uint64_t acc = dh_mul2(q01, ka.x);
+                acc = dh_fma2(q23, ka.y, acc); acc = dh_fma2(q45, kb.x, acc); acc = dh_fma2(q67, kb.y, acc);
+                float lo, hi;
+                dh_unpk(acc, lo, hi);
+                const float v = lo + hi;
                 s[j] = v;
                 cm = fmaxf(cm, v);
             }
@@ -322,19 +334,24 @@ __device__ __forceinline__ void dh_attention(uint32_t tmem, const float* s_kv, u
             const float sc = dh_ex2(mx - mn);   // first chunk: 2^(-inf) = 0
             mx = mn;
             sum *= sc;
+            const uint64_t sc2 = dh_pk(sc, sc);
 #pragma unroll
-            for (int d = 0; d < 8; ++d) o[d] *= sc;
+            for (int d = 0; d < 4; ++d) o2[d] = dh_mul2(o2[d], sc2);
 #pragma unroll
-            for (int j = 0; j < 30; ++j) {
+            for (int j = 0; j < DH_CHUNK; ++j) {
                 const float p = dh_ex2(s[j] - mn);
                 sum += p;
+                const uint64_t p2 = dh_pk(p, p);
                 const float* vr = s_kv + (base + j0 + j) * DH_LDKV + 64 + h * 8;
-                const float4 va = *reinterpret_cast<const float4*>(vr);
-                const float4 vb = *reinterpret_cast<const float4*>(vr + 4);
-                o[0] = fmaf(p, va.x, o[0]); o[1] = fmaf(p, va.y, o[1]); o[2] = fmaf(p, va.z, o[2]); o[3] = fmaf(p, va.w, o[3]);
-                o[4] = fmaf(p, vb.x, o[4]); o[5] = fmaf(p, vb.y, o[5]); o[6] = fmaf(p, vb.z, o[6]); o[7] = fmaf(p, vb.w, o[7]);
+                const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(vr);
+                const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(vr + 4);
+                o2[0] = dh_fma2(p2, va.x, o2[0]); o2[1] = dh_fma2(p2, va.y, o2[1]);
+                o2[2] = dh_fma2(p2, vb.x, o2[2]); o2[3] = dh_fma2(p2, vb.y, o2[3]);
             }
         }
+        float o[8];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) dh_unpk(o2[d], o[2 * d], o[2 * d + 1]);
         if (valid) {
             const float inv = 1.0f / sum;
 #pragma unroll

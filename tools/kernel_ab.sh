@@ -1,13 +1,13 @@
 #!/bin/bash
 # A/B of an experimental CUDA source against the shipping one of the same name: builds a scratch copy of the library in which
 # etch_b200/csrc/<name>.cu is replaced by <variant.cu> and prints the per-kernel CUDA-event times of one eager step at the bench shape.
-#   bash tools/kernel_ab.sh pt_tc /tmp/pt_tc_variant.cu pt_attention_tc
+#   bash tools/kernel_ab.sh pt_tc /tmp/pt_tc_variant.cu pt_attention_tc [more_variants.cu ...]
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 cd "$ROOT"
-NAME=$1; VARIANT=$2; KEY=$3
+NAME=$1; VARIANT=$2; KEY=$3; shift 3
 python -m etch_b200.build > /dev/null
-for src in etch_b200/csrc/$NAME.cu "$VARIANT"; do
+for src in etch_b200/csrc/$NAME.cu "$VARIANT" "$@"; do
   tag=$(basename ${src%.cu})_$(echo $src | md5sum | cut -c1-6)
   o=/tmp/ab_$tag.o
   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -I include -I etch_b200/csrc -c $src -o $o 2>/dev/null
