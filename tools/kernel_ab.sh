@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of an experimental CUDA source against the shipping one of the same name: builds a scratch copy of the library in which
 # etch_b200/csrc/<name>.cu is replaced by <variant.cu> and prints the per-kernel CUDA-event times of one eager step at the bench shape.
-#   bash tools/kernel_ab.sh pt_tc /tmp/pt_tc_variant.cu pt_attention_tc [more_variants.cu ...]
+#   bash tools/kernel_ab.sh pt_tc /tmp/pt_tc_variant.cu pt_attention_tc [more_variants.cu ...]   (the kernel key may be a comma-separated list)
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 cd "$ROOT"
@@ -31,6 +31,6 @@ for rep in range(4):
     L.start_profile(); out = pipe.eager(pts); prof = L.stop_profile()
     for k, (c, t) in prof.items():
         best[k] = min(best.get(k, 1e9), t)
-print("$src: $KEY %.3f ms; step sum %.2f ms; checksum %.6f" % (best["$KEY"], sum(best.values()), out["vertices"][torch.isfinite(out["vertices"]).all(-1).all(-1)].double().abs().mean().item()), flush=True)
+print("$src: %s ms; step sum %.2f ms; checksum %.6f" % (" ".join("%s %.3f" % (k, best[k]) for k in "$KEY".split(",")), sum(best.values()), out["vertices"][torch.isfinite(out["vertices"]).all(-1).all(-1)].double().abs().mean().item()), flush=True)
 PY
 done
