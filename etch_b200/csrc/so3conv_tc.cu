@@ -166,17 +166,38 @@ __global__ void __launch_bounds__(288, (AgemmCfg<CIN, COUT, J>::CTAS_PER_SM)) an
                 const uint32_t ab = g & 1;
                 if (g >= 2) umma::mbar_wait(&a_free[ab], ((g >> 1) - 1) & 1);
                 if (fok) {   // rows 120..127 are never written: their (garbage) products land in TMEM rows that are never read
-                    const float* xr = s_x + (fpl * NA + s_tab[fa * J + j]) * LD + fhalf * (CIN / 2);
+                    const int srow = fpl * NA + s_tab[fa * J + j];
                     unsigned char* dh = s_A + ab * 2 * A_BYTES + frow * 16;
+                    if constexpr (CIN == 32) {
+                        // The 8 lanes of a quarter warp gather 8 arbitrary source rows; at the same column two rows that are congruent
+                        // mod 8 share a 16-byte bank group (row stride = 9 groups), which doubled the wavefronts of this load (ncu:
+                        // 29.4 M for 14.4 M ideal).  Lane l of thread half f therefore takes the chunk that lies in bank group
+                        // (l + 4 f + i) mod 8 at step i: the quarter warp covers all 8 groups at every step and the two halves cover
+                        // the 8 chunks of a row between them.
+                        const float* xr = s_x + srow * LD;
+                        const int rot = lane + 4 * fhalf - srow;
 #pragma unroll
-                    for (int c4 = 0; c4 < CIN / 8; ++c4) {
-                        const float4 v = *reinterpret_cast<const float4*>(xr + c4 * 4);
-                        float4 h, l;
-                        umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
-                        umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
-                        const int kc = fhalf * (CIN / 8) + c4;
-                        *reinterpret_cast<float4*>(dh + kc * (MROWS * 16)) = h;
-                        *reinterpret_cast<float4*>(dh + A_BYTES + kc * (MROWS * 16)) = l;
+                        for (int i = 0; i < 4; ++i) {
+                            const int c4 = (rot + i) & 7;
+                            const float4 v = *reinterpret_cast<const float4*>(xr + c4 * 4);
+                            float4 h, l;
+                            umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+                            umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+                            *reinterpret_cast<float4*>(dh + c4 * (MROWS * 16)) = h;
+                            *reinterpret_cast<float4*>(dh + A_BYTES + c4 * (MROWS * 16)) = l;
+                        }
+                    } else {
+                        const float* xr = s_x + srow * LD + fhalf * (CIN / 2);
+#pragma unroll
+                        for (int c4 = 0; c4 < CIN / 8; ++c4) {
+                            const float4 v = *reinterpret_cast<const float4*>(xr + c4 * 4);
+                            float4 h, l;
+                            umma::split_tf32(v.x, h.x, l.x); umma::split_tf32(v.y, h.y, l.y);
+                            umma::split_tf32(v.z, h.z, l.z); umma::split_tf32(v.w, h.w, l.w);
+                            const int kc = fhalf * (CIN / 8) + c4;
+                            *reinterpret_cast<float4*>(dh + kc * (MROWS * 16)) = h;
+                            *reinterpret_cast<float4*>(dh + A_BYTES + kc * (MROWS * 16)) = l;
+                        }
                     }
                 }
                 umma::fence_async_smem();
@@ -199,19 +220,23 @@ __global__ void __launch_bounds__(288, (AgemmCfg<CIN, COUT, J>::CTAS_PER_SM)) an
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
                     o0 = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
                     o1 = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
-                    *reinterpret_cast<float4*>(s_z + row * COUT + col) = o0;
-                    *reinterpret_cast<float4*>(s_z + row * COUT + col + 4) = o1;
+                    // 16-byte chunk ch of row r sits at chunk (ch ^ (r & 7)): the row stride is a multiple of 128 B, so the unswizzled
+                    // stores of 8 consecutive rows all hit one bank group (ncu: 8-way conflicts on both stores)
+                    *reinterpret_cast<float4*>(s_z + row * COUT + (((col >> 2) ^ (row & 7)) << 2)) = o0;
+                    *reinterpret_cast<float4*>(s_z + row * COUT + ((((col >> 2) + 1) ^ (row & 7)) << 2)) = o1;
                 }
             }
             umma::fence_before_sync();
             compute_warps_sync();
             const int nvalid = npts * NA;
             float* dst = zraw + ((size_t)b * P + p0) * NA * COUT;
-            for (int i = tid; i < nvalid * COUT / 4; i += 256)
-                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_z)[i];
+            for (int i = tid; i < nvalid * COUT / 4; i += 256) {
+                const int r = i / (COUT / 4), ch = i % (COUT / 4);
+                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_z)[r * (COUT / 4) + (ch ^ (r & 7))];
+            }
             {
                 float s = 0.f, ss = 0.f;
-                for (int r = srg; r < nvalid; r += RG) { const float v = s_z[r * COUT + scol]; s += v; ss = fmaf(v, v, ss); }
+                for (int r = srg; r < nvalid; r += RG) { const float v = s_z[r * COUT + ((((scol >> 2) ^ (r & 7)) << 2) | (scol & 3))]; s += v; ss = fmaf(v, v, ss); }
                 acc_s += (double)s; acc_ss += (double)ss;
             }
             compute_warps_sync();   // s_z (= A ring) and s_x are free for the next tile
