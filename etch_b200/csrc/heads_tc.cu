@@ -183,7 +183,6 @@ constexpr int DH_CHUNK = 60;                       // keys per online-softmax ch
 constexpr int DH_LDKV = 132;                       // floats per row of the K|V tile
 constexpr uint32_t DH_XB = 128 * 64 * 4;           // bytes of one canonical [128 x 64] tile
 constexpr uint32_t DH_WB = 64 * 32 * 4;            // bytes of one (hi or lo) weight slice [64 rows x 32 k]
-constexpr int DH_NCHUNK = 18;
 
 __device__ void dh_jacobi3(double A[3][3], double V[3][3], double e[3]) {
     for (int i = 0; i < 3; ++i)
@@ -233,37 +232,35 @@ __device__ void dh_so3_direction(const double Ce[3][3], float out[3]) {
     for (int i = 0; i < 3; ++i) out[i] = (float)(u0[i] * v0[2] + u1[i] * v1[2] + u2[i] * v2z);
 }
 
-struct DhIssuer {   // state of the weight-streaming / MMA-issuing warp (all fields warp-uniform)
+// Weight streaming of the MMA-issuing warp.  A tile consumes 18 [64 rows x 32 k] (hi|lo) slices in a fixed order (n = 0..17: K, V, Q
+// blocks of layer 1, head-combine, K, V, Q of layer 2, the two blocks of the fused MLP).  Shared memory is full, so besides the two
+// dedicated slots B0, B1 the slices land in storage that is dead at that point of the tile: the attention-output tile O (4 slots: dead
+// from the end of the MLP MMAs until the next attention writes it) and the K|V tile (3 slots: dead between an attention and the next
+// K|V copy).  Every load is issued at a program point where its slot is known to be free (after the mbarrier that tracks the MMAs which
+// read it), so there are no "empty" barriers; slot s signals arrival on full[s], whose parity follows from the number of uses per tile.
+//   n      : 0  1  2  3  4  5 | 6  7 | 8   9   10  11 12 13 | 14 15 16  17
+//   slot   : O0 O1 O2 O3 B0 B1| B0 B1| KV0 KV1 KV2 B0 B1 O0 | B0 B1 KV0 KV1
+struct DhSlots {
     const float* wall;      // [18][2][8][64][4]: 9 blocks of 64 output rows x 2 K-halves, (hi, lo) canonical tiles
-    unsigned char* s_B;     // [2][hi|lo]
-    uint64_t* b_full;
-    uint64_t* b_empty;
-    uint32_t gl, gm;        // global load / mma counters (ring phases run across tiles)
-    int ld;                 // slices loaded in the current tile
-    __device__ void load_next() {
-        if (ld >= DH_NCHUNK) return;
-        const uint32_t buf = gl & 1;
-        if (gl >= 2) umma::mbar_wait(&b_empty[buf], ((gl - 2) >> 1) & 1);
-        // streaming order: K and V blocks before the Q block of a QKV phase (K|V are copied to shared memory under the Q MMAs)
-        const int sl = ld < 6 ? (ld < 4 ? ld + 2 : ld - 4) : (ld >= 8 && ld < 14 ? (ld < 12 ? ld + 2 : ld - 4) : ld);
-        umma::bulk_load(s_B + buf * 2 * DH_WB, wall + (size_t)sl * 2 * 64 * 32, 2 * DH_WB, &b_full[buf]);
-        ++ld; ++gl;
+    unsigned char *s_B, *s_O, *s_KV;
+    uint64_t* full;         // [9]: B0 B1 O0 O1 O2 O3 KV0 KV1 KV2
+    __device__ unsigned char* addr(int slot) const {
+        return slot < 2 ? s_B + slot * 2 * DH_WB : slot < 6 ? s_O + (slot - 2) * 2 * DH_WB : s_KV + (slot - 6) * 2 * DH_WB;
     }
-    // one 64-column block of the output = two slices (K halves 0..31, 32..63) accumulated into tmem_d[0:64]
-    __device__ void mma_block(uint32_t a_hi, uint32_t a_lo, uint32_t tmem_d) {
-        for (int kh = 0; kh < 2; ++kh) {
-            const uint32_t buf = gm & 1;
-            umma::mbar_wait(&b_full[buf], (gm >> 1) & 1);
-            umma::fence_after_sync();
-            const uint32_t b_hi = umma::smem_u32(s_B + buf * 2 * DH_WB), b_lo = b_hi + DH_WB;
-            // K-half kh of the canonical [128 x 64] A tile starts (32/4) k-chunks = 8 * 2048 bytes in
-            umma::issue_gemm_3xtf32(tmem_d, a_hi + kh * 8 * 2048, a_lo + kh * 8 * 2048, b_hi, b_lo, 32, 64, kh > 0);
-            umma::commit(&b_empty[buf]);
-            ++gm;
-            load_next();
-        }
+    // consumption index -> slice of `wall` (the K and V blocks of a QKV projection are consumed before its Q block)
+    static __device__ int phys(int n) { return n < 6 ? (n < 4 ? n + 2 : n - 4) : (n >= 8 && n < 14 ? (n < 12 ? n + 2 : n - 4) : n); }
+    __device__ void load(int n, int slot) const {
+        umma::bulk_load(addr(slot), wall + (size_t)phys(n) * 2 * 64 * 32, 2 * DH_WB, &full[slot]);
+    }
+    // K-half kh of a 64-column output block: A = K-half kh of the canonical [128 x 64] tile ((32/4) k-chunks = 8 * 2048 bytes in)
+    __device__ void mma(int slot, uint32_t parity, uint32_t a_hi, uint32_t a_lo, uint32_t tmem_d, int kh) const {
+        umma::mbar_wait(&full[slot], parity);
+        umma::fence_after_sync();
+        const uint32_t b_hi = umma::smem_u32(addr(slot)), b_lo = b_hi + DH_WB;
+        umma::issue_gemm_3xtf32(tmem_d, a_hi + kh * 8 * 2048, a_lo + kh * 8 * 2048, b_hi, b_lo, 32, 64, kh > 0);
     }
 };
+enum { SB0 = 0, SB1 = 1, SO0 = 2, SO1 = 3, SO2 = 4, SO3 = 5, SKV0 = 6, SKV1 = 7, SKV2 = 8 };
 
 // K (warps 0-3) / V (warps 4-7) columns of the QKV accumulator -> token-major shared tile
 __device__ __forceinline__ void dh_store_kv(uint32_t tmem, float* s_kv, int warp, int lane) {
@@ -386,7 +383,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     float* s_w = s_part + 256;                             // [128]
     float* s_anc = s_w + 128;                              // [60][9]
     __shared__ __align__(16) float s_bc1[64], s_bf[128], s_vreg[128];
-    __shared__ uint64_t b_full[2], b_empty[2], bar_mma, bar_kv;
+    __shared__ uint64_t s_full[9], bar_mma, bar_kv;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < DH_NA * 9; i += 256) s_anc[i] = __ldg(anchors + i);
@@ -394,8 +391,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     if (tid < 128) { s_bf[tid] = __ldg(bf + tid); s_vreg[tid] = __ldg(vreg + tid); }
     if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
     if (tid == 0) {
-        umma::mbar_init(&b_full[0], 1); umma::mbar_init(&b_full[1], 1);
-        umma::mbar_init(&b_empty[0], 1); umma::mbar_init(&b_empty[1], 1);
+        for (int i = 0; i < 9; ++i) umma::mbar_init(&s_full[i], 1);
         umma::mbar_init(&bar_mma, 1); umma::mbar_init(&bar_kv, 1);
     }
     umma::fence_before_sync();
@@ -403,68 +399,95 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     umma::fence_after_sync();
     const uint32_t tmem = umma::uniform(tmem_base);
     const uint32_t x_hi = umma::smem_u32(s_X), x_lo = x_hi + DH_XB, o_hi = umma::smem_u32(s_O), o_lo = o_hi + DH_XB;
-    DhIssuer iss{wall, s_B, b_full, b_empty, 0u, 0u, 0};
+    const DhSlots iss{wall, s_B, s_O, reinterpret_cast<unsigned char*>(s_kv), s_full};
+    static_assert(3 * 2 * DH_WB <= 2 * DH_NA * DH_LDKV * 4, "three slice slots fit the K|V tile");
     uint32_t n_mma = 0, n_kv = 0;
     const int ntiles = (N + 1) / 2;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
 
-    auto blend = [&](int g) {
+    // Blend of a tile's tokens (3 coarse rows per token, interpolation weights from the 3-NN search) into X as (hi, lo).  The 24 loads
+    // of a thread are issued back to back (one L2 round trip instead of three, the neighbour ids and weights were fetched a tile ahead)
+    // and consumed later: the ncu source view had 17 % of the kernel's stall samples on these loads.
+    const int br = tid & 127, bhf = tid >> 7;             // token row, channel half
+    const bool brow_ok = br < 2 * DH_NA;
+    const int bpl = brow_ok ? br / DH_NA : 0, ba = brow_ok ? br % DH_NA : 0;
+    int nb_idx[3] = {0, 0, 0};
+    float nb_w[3] = {0.f, 0.f, 0.f};
+    float4 bv[3][8];
+    auto blend_ids = [&](int g) {
         const int b = g / ntiles, tile = g - b * ntiles;
-        const float* F = feats + (size_t)b * S * DH_NA * 64;
-        const int p0 = tile * 2;
-        // ---- 0. blend the three coarse rows into the token tile (hi/lo, canonical) ----
-        {
-            const int r = tid >> 1, hf = tid & 1;
-            float4 acc[8];
+        const int p = min(tile * 2 + bpl, N - 1);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < 2 * DH_NA) {
-                const int pl = r / DH_NA, a = r % DH_NA;
-                const int p = min(p0 + pl, N - 1);
-                const int* ip = up_idx + ((size_t)b * N + p) * 3;
-                const float* wp = up_w + ((size_t)b * N + p) * 3;
+        for (int k = 0; k < 3; ++k) {
+            nb_idx[k] = __ldg(up_idx + ((size_t)b * N + p) * 3 + k);
+            nb_w[k] = __ldg(up_w + ((size_t)b * N + p) * 3 + k);
+        }
+    };
+    auto blend_load = [&](int g) {
+        const float* F = feats + (size_t)(g / ntiles) * S * DH_NA * 64;
+        if (brow_ok) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float wk = __ldg(wp + k);
-                    const float4* src = reinterpret_cast<const float4*>(F + ((size_t)__ldg(ip + k) * DH_NA + a) * 64 + hf * 32);
+            for (int k = 0; k < 3; ++k) {
+                const float4* src = reinterpret_cast<const float4*>(F + ((size_t)nb_idx[k] * DH_NA + ba) * 64 + bhf * 32);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 v = __ldg(src + i);
-                        acc[i].x = fmaf(v.x, wk, acc[i].x); acc[i].y = fmaf(v.y, wk, acc[i].y);
-                        acc[i].z = fmaf(v.z, wk, acc[i].z); acc[i].w = fmaf(v.w, wk, acc[i].w);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 hi, lo;
-                umma::split_tf32(acc[i].x, hi.x, lo.x); umma::split_tf32(acc[i].y, hi.y, lo.y);
-                umma::split_tf32(acc[i].z, hi.z, lo.z); umma::split_tf32(acc[i].w, hi.w, lo.w);
-                const int kc = hf * 8 + i;
-                *reinterpret_cast<float4*>(s_X + kc * (128 * 16) + r * 16) = hi;
-                *reinterpret_cast<float4*>(s_X + DH_XB + kc * (128 * 16) + r * 16) = lo;
+                for (int i = 0; i < 8; ++i) bv[k][i] = __ldg(src + i);
             }
         }
     };
+    auto blend_store = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (brow_ok) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    acc.x = fmaf(bv[k][i].x, nb_w[k], acc.x); acc.y = fmaf(bv[k][i].y, nb_w[k], acc.y);
+                    acc.z = fmaf(bv[k][i].z, nb_w[k], acc.z); acc.w = fmaf(bv[k][i].w, nb_w[k], acc.w);
+                }
+            }
+            float4 hi, lo;
+            umma::split_tf32(acc.x, hi.x, lo.x); umma::split_tf32(acc.y, hi.y, lo.y);
+            umma::split_tf32(acc.z, hi.z, lo.z); umma::split_tf32(acc.w, hi.w, lo.w);
+            const int kc = bhf * 8 + i;
+            *reinterpret_cast<float4*>(s_X + kc * (128 * 16) + br * 16) = hi;
+            *reinterpret_cast<float4*>(s_X + DH_XB + kc * (128 * 16) + br * 16) = lo;
+        }
+    };
+    const int total_tiles = ntiles * nscans;
+    if ((int)blockIdx.x < total_tiles) {
+        if (warp == 0) {   // slices of the first tile's QKV projection
+            iss.load(0, SO0); iss.load(1, SO1); iss.load(2, SO2); iss.load(3, SO3); iss.load(4, SB0); iss.load(5, SB1);
+        }
+        blend_ids(blockIdx.x);
+        blend_load(blockIdx.x);
+        blend_store();
+    }
+    uint32_t tp = 0;   // parity of this CTA's tile counter (slots used once per tile)
 
     // scan-major tile sequence: the whole grid blends from one scan's coarse features at a time (19 MB, L2 resident) instead of
     // all B of them (the scan-parallel grid re-read them 4x from DRAM)
-    for (int gt = blockIdx.x; gt < ntiles * nscans; gt += gridDim.x) {
+    for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
         const int b = gt / ntiles, tile = gt - b * ntiles;
-        const float* F = feats + (size_t)b * S * DH_NA * 64;
         const int p0 = tile * 2;
-        if (warp == 0) { iss.ld = 0; iss.load_next(); iss.load_next(); }
-        if (gt == (int)blockIdx.x) blend(gt);   // later tiles are blended under the previous tile's last MMAs
+        const bool has_next = gt + (int)gridDim.x < total_tiles;
+        if (has_next) blend_ids(gt + gridDim.x);   // neighbour ids / weights of the next tile: in registers long before its blend
         for (int layer = 0; layer < 2; ++layer) {
             umma::fence_async_smem();
             __syncthreads();
-            // ---- QKV projection: 6 slices -> D[0:192] ----
+            // ---- QKV projection: 6 slices -> D[0:192]; K and V first, they are copied to shared memory under the Q MMAs ----
             if (warp == 0) {
                 umma::fence_after_sync();
-                iss.mma_block(x_hi, x_lo, tmem + 64);
-                iss.mma_block(x_hi, x_lo, tmem + 128);
-                umma::commit(&bar_kv);
-                iss.mma_block(x_hi, x_lo, tmem);
+                if (layer == 0) {
+                    iss.mma(SO0, 0, x_hi, x_lo, tmem + 64, 0);   iss.mma(SO1, tp, x_hi, x_lo, tmem + 64, 1);
+                    iss.mma(SO2, tp, x_hi, x_lo, tmem + 128, 0); iss.mma(SO3, tp, x_hi, x_lo, tmem + 128, 1);
+                    umma::commit(&bar_kv);
+                    iss.mma(SB0, 0, x_hi, x_lo, tmem, 0);        iss.mma(SB1, 0, x_hi, x_lo, tmem, 1);
+                } else {
+                    iss.mma(SKV0, 0, x_hi, x_lo, tmem + 64, 0);   iss.mma(SKV1, 0, x_hi, x_lo, tmem + 64, 1);
+                    iss.mma(SKV2, tp, x_hi, x_lo, tmem + 128, 0); iss.mma(SB0, 0, x_hi, x_lo, tmem + 128, 1);
+                    umma::commit(&bar_kv);
+                    iss.mma(SB1, 0, x_hi, x_lo, tmem, 0);         iss.mma(SO0, 1, x_hi, x_lo, tmem, 1);
+                }
                 umma::commit(&bar_mma);
             }
             umma::mbar_wait(&bar_kv, n_kv & 1); ++n_kv;
@@ -472,6 +495,10 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
             dh_store_kv(tmem, s_kv, warp, lane);
             umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
             umma::fence_after_sync();
+            if (warp == 0) {   // B0 / B1 are free: head-combine slices (layer 1) or the first MLP block (layer 2)
+                if (layer == 0) { iss.load(6, SB0); iss.load(7, SB1); }
+                else { iss.load(14, SB0); iss.load(15, SB1); }
+            }
             __syncthreads();
             dh_attention(tmem, s_kv, s_O, warp, lane);
             umma::fence_before_sync();
@@ -481,11 +508,14 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
                 // ---- head_combine + bias + residual -> X ----
                 if (warp == 0) {
                     umma::fence_after_sync();
-                    iss.mma_block(o_hi, o_lo, tmem + 192);
+                    // the K|V tile is dead until the next K|V copy: it takes the first three slices of layer 2's projection
+                    iss.load(8, SKV0); iss.load(9, SKV1); iss.load(10, SKV2);
+                    iss.mma(SB0, 1, o_hi, o_lo, tmem + 192, 0); iss.mma(SB1, 1, o_hi, o_lo, tmem + 192, 1);
                     umma::commit(&bar_mma);
                 }
                 umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
                 umma::fence_after_sync();
+                if (warp == 0) { iss.load(11, SB0); iss.load(12, SB1); iss.load(13, SO0); }   // O is dead until the next attention
                 float v[32];
                 umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 192 + half * 32, v);
 #pragma unroll
@@ -508,13 +538,19 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
         // ---- fused (Linear1 o head_combine_2) + ReLU, then (so3_reg o Linear2): D[256:384] -> anchor weights ----
         if (warp == 0) {
             umma::fence_after_sync();
-            for (int c = 0; c < 2; ++c) iss.mma_block(o_hi, o_lo, tmem + 256 + c * 64);
+            iss.load(16, SKV0); iss.load(17, SKV1);   // second MLP block: the K|V tile is dead again
+            iss.mma(SB0, 1, o_hi, o_lo, tmem + 256, 0);  iss.mma(SB1, 1, o_hi, o_lo, tmem + 256, 1);
+            iss.mma(SKV0, 1, o_hi, o_lo, tmem + 320, 0); iss.mma(SKV1, 1, o_hi, o_lo, tmem + 320, 1);
             umma::commit(&bar_mma);
         }
         // X is dead since the layer-2 QKV MMAs completed: blend the next tile's tokens while the last MMAs run
-        if (gt + (int)gridDim.x < ntiles * nscans) blend(gt + gridDim.x);
+        if (has_next) { blend_load(gt + gridDim.x); blend_store(); }
         umma::mbar_wait(&bar_mma, n_mma & 1); ++n_mma;
         umma::fence_after_sync();
+        if (has_next && warp == 0) {   // O, B0, B1 are free: the next tile's QKV slices arrive under this tile's epilogue
+            iss.load(0, SO0); iss.load(1, SO1); iss.load(2, SO2); iss.load(3, SO3); iss.load(4, SB0); iss.load(5, SB1);
+        }
+        tp ^= 1;
         {
             float part = 0.f;
 #pragma unroll

@@ -325,8 +325,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
                 umma::tmem_ld8(tmem + tlane + COUT + c0, u);
                 if (ok) {
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-                    *reinterpret_cast<float4*>(s_z + row * COUT + c0) = make_float4(v[0] + u[0] + b0.x, v[1] + u[1] + b0.y, v[2] + u[2] + b0.z, v[3] + u[3] + b0.w);
-                    *reinterpret_cast<float4*>(s_z + row * COUT + c0 + 4) = make_float4(v[4] + u[4] + b1.x, v[5] + u[5] + b1.y, v[6] + u[6] + b1.z, v[7] + u[7] + b1.w);
+                    *reinterpret_cast<float4*>(s_z + row * COUT + (((c0 >> 2) ^ (row & 7)) << 2)) = make_float4(v[0] + u[0] + b0.x, v[1] + u[1] + b0.y, v[2] + u[2] + b0.z, v[3] + u[3] + b0.w);
+                    *reinterpret_cast<float4*>(s_z + row * COUT + ((((c0 >> 2) + 1) ^ (row & 7)) << 2)) = make_float4(v[4] + u[4] + b1.x, v[5] + u[5] + b1.y, v[6] + u[6] + b1.z, v[7] + u[7] + b1.w);
                 }
             }
             umma::fence_before_sync();
@@ -335,10 +335,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) inter_conv_v3_kernel(
             bar_sync_named(2, 128);
             const size_t gp = (size_t)blockIdx.x + (size_t)pi * gridDim.x, b = gp / (size_t)P;
             float4* dst = reinterpret_cast<float4*>(zraw + gp * NA * COUT);
-            for (int i = t; i < NA * COUT / 4; i += 128) dst[i] = reinterpret_cast<const float4*>(s_z)[i];
+            for (int i = t; i < NA * COUT / 4; i += 128) {   // the tile is XOR-swizzled by (row & 7): its row stride is a multiple of 128 B
+                const int r = i / (COUT / 4), ch = i % (COUT / 4);
+                dst[i] = reinterpret_cast<const float4*>(s_z)[r * (COUT / 4) + (ch ^ (r & 7))];
+            }
             if (t < COUT) {
                 float s = 0.f, ss = 0.f;
-                for (int r = 0; r < NA; ++r) { const float x = s_z[r * COUT + t]; s += x; ss = fmaf(x, x, ss); }
+                for (int r = 0; r < NA; ++r) { const float x = s_z[r * COUT + ((((t >> 2) ^ (r & 7)) << 2) | (t & 3))]; s += x; ss = fmaf(x, x, ss); }
                 s_stat[2 * t] += (double)s; s_stat[2 * t + 1] += (double)ss;
                 if (pi + 1 == (uint32_t)npts || (gp + gridDim.x) / (size_t)P != b) {   // last point of this scan for this CTA: flush its statistics
                     atomicAdd(stats + (b * COUT + t) * 2, s_stat[2 * t]);
