@@ -240,6 +240,15 @@ __device__ void dh_so3_direction(const double Ce[3][3], float out[3]) {
 // read it), so there are no "empty" barriers; slot s signals arrival on full[s], whose parity follows from the number of uses per tile.
 //   n      : 0  1  2  3  4  5 | 6  7 | 8   9   10  11 12 13 | 14 15 16  17
 //   slot   : O0 O1 O2 O3 B0 B1| B0 B1| KV0 KV1 KV2 B0 B1 O0 | B0 B1 KV0 KV1
+// 256-bit global load that does not allocate in L1: every 32-byte sector of the coarse features is read exactly once per tile, and with
+// the 227 KB shared-memory carve-out the few L1 lines that are left throttled the blend (A/B: 128-bit __ldg 4.50 ms, 256-bit 4.32 ms,
+// 256-bit no-allocate 4.17 ms; coalescing the rows across lanes changed nothing: the LSU queue counts instructions)
+__device__ __forceinline__ void dh_ld256(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
 struct DhSlots {
     const float* wall;      // [18][2][8][64][4]: 9 blocks of 64 output rows x 2 K-halves, (hi, lo) canonical tiles
     unsigned char *s_B, *s_O, *s_KV;
@@ -405,9 +414,9 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
     const int ntiles = (N + 1) / 2;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
 
-    // Blend of a tile's tokens (3 coarse rows per token, interpolation weights from the 3-NN search) into X as (hi, lo).  The 24 loads
+    // Blend of a tile's tokens (3 coarse rows per token, interpolation weights from the 3-NN search) into X as (hi, lo).  The 12 loads
     // of a thread are issued back to back (one L2 round trip instead of three, the neighbour ids and weights were fetched a tile ahead)
-    // and consumed later: the ncu source view had 17 % of the kernel's stall samples on these loads.
+    // and consumed later: the ncu source view had 17-22 % of the kernel's stall samples on these loads (LSU queue throttle).
     const int br = tid & 127, bhf = tid >> 7;             // token row, channel half
     const bool brow_ok = br < 2 * DH_NA;
     const int bpl = brow_ok ? br / DH_NA : 0, ba = brow_ok ? br % DH_NA : 0;
@@ -428,9 +437,14 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
         if (brow_ok) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4* src = reinterpret_cast<const float4*>(F + ((size_t)nb_idx[k] * DH_NA + ba) * 64 + bhf * 32);
+                const float* src = F + ((size_t)nb_idx[k] * DH_NA + ba) * 64 + bhf * 32;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) bv[k][i] = __ldg(src + i);
+                for (int i = 0; i < 8; i += 2) {
+                    float t8[8];
+                    dh_ld256(src + i * 4, t8);
+                    bv[k][i] = make_float4(t8[0], t8[1], t8[2], t8[3]);
+                    bv[k][i + 1] = make_float4(t8[4], t8[5], t8[6], t8[7]);
+                }
             }
         }
     };
