@@ -55,6 +55,15 @@ __global__ void __launch_bounds__(256, 1) linear_tc_kernel(const float* __restri
         const int gm_row = tile * 128 + frow;
         const int k0 = kc * 32 + fhalf * 16;
         const float* src = X + (size_t)(gm_row < n ? gm_row : 0) * ldx + k0;
+        if (gm_row < n && k0 + 15 < ci && ((reinterpret_cast<uintptr_t>(src) & 31) == 0)) {
+            // the common case: two 256-bit loads that do not allocate in L1 (X is streamed once per CTA; see etch_ld256_na)
+            float a8[8], b8[8];
+            etch_ld256_na(src, a8);
+            etch_ld256_na(src + 8, b8);
+            v[0] = make_float4(a8[0], a8[1], a8[2], a8[3]); v[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+            v[2] = make_float4(b8[0], b8[1], b8[2], b8[3]); v[3] = make_float4(b8[4], b8[5], b8[6], b8[7]);
+            return;
+        }
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
             const int k = k0 + c4 * 4;

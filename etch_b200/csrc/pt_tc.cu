@@ -125,11 +125,15 @@ __global__ void __launch_bounds__(256) pt_attn_tc_kernel(const float* __restrict
                                         &w_full[(n_w + ch + 1) & 1]);
                 }
                 const int c0 = ch * PT_KC + half * 32;
-#pragma unroll 4
+                // the k row of a (point, neighbour) pair is read once: four 256-bit loads that do not allocate in L1, all in flight
+                float k8[4][8];
+#pragma unroll
+                for (int g2 = 0; g2 < 4; ++g2) etch_ld256_na(krow + c0 + g2 * 8, k8[g2]);
+#pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    const float4 kv = __ldg(reinterpret_cast<const float4*>(krow + c0) + g);
                     const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow + c0) + g);
-                    const float kk[4] = {kv.x, kv.y, kv.z, kv.w}, qq[4] = {qv.x, qv.y, qv.z, qv.w};
+                    const float kk[4] = {k8[g >> 1][(g & 1) * 4], k8[g >> 1][(g & 1) * 4 + 1], k8[g >> 1][(g & 1) * 4 + 2], k8[g >> 1][(g & 1) * 4 + 3]};
+                    const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
                     float hi[4], lo[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
