@@ -172,10 +172,11 @@ ETCH_API int etch_conf_head_tc(const float* x, const float* logits, const float*
 //   D[256:384] = O  (W1 Wc2)^T        (layer 2 output folded with Linear1; ReLU and the 128->1 map are applied straight
 //                                      from TMEM, the hidden layer is never stored)
 // Activations live in shared memory as (hi, lo) TF32 pairs in the canonical UMMA layout (x == hi + lo exactly), weights
-// stream as 18 pre-split [64 rows x 32 k] slices per tile through a 2-deep cp.async.bulk ring.  The softmax attention itself is
-// block-diagonal (60x60 per point and head) and stays on the CUDA cores.  Two overlaps inside a tile: the K and V blocks of a QKV
-// projection are issued before the Q block, so K|V move to shared memory under the Q MMAs, and the NEXT tile's tokens are blended
-// into X (dead once the layer-2 QKV MMAs have completed) while the last two MMA blocks of the current tile run.
+// stream as 18 pre-split [64 rows x 32 k] slices per tile (cp.async.bulk) into two dedicated slots plus storage that is dead at that
+// point of the tile (DhSlots below).  The softmax attention itself is block-diagonal (60x60 per point and head) and stays on the
+// CUDA cores (packed fma.rn.f32x2).  Overlaps inside a tile: the K and V blocks of a QKV projection are issued before the Q block,
+// so K|V move to shared memory under the Q MMAs; the NEXT tile's tokens are blended into X (dead once the layer-2 QKV MMAs have
+// completed) while the last two MMA blocks of the current tile run; the next tile's QKV slices travel under the epilogue.
 namespace {
 
 constexpr int DH_NA = 60;
