@@ -55,15 +55,10 @@ __device__ __forceinline__ void etch_ldg256(const float* p, float (&v)[8]) {
                  : "l"(p));
 }
 
-// 256-bit / 128-bit global loads that do not allocate in L1 (data read once per CTA: with a 200+ KB shared-memory carve-out the few L1
+// 256-bit global load that does not allocate in L1 (data read once per CTA: with a 200+ KB shared-memory carve-out the few L1
 // lines that are left throttle the LSU queue; see the direction-head blend in heads_tc.cu)
 __device__ __forceinline__ void etch_ld256_na(const float* p, float (&v)[8]) {
     asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
-}
-__device__ __forceinline__ float4 etch_ld128_na(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
 }
