@@ -241,15 +241,6 @@ __device__ void dh_so3_direction(const double Ce[3][3], float out[3]) {
 // read it), so there are no "empty" barriers; slot s signals arrival on full[s], whose parity follows from the number of uses per tile.
 //   n      : 0  1  2  3  4  5 | 6  7 | 8   9   10  11 12 13 | 14 15 16  17
 //   slot   : O0 O1 O2 O3 B0 B1| B0 B1| KV0 KV1 KV2 B0 B1 O0 | B0 B1 KV0 KV1
-// 256-bit global load that does not allocate in L1: every 32-byte sector of the coarse features is read exactly once per tile, and with
-// the 227 KB shared-memory carve-out the few L1 lines that are left throttled the blend (A/B: 128-bit __ldg 4.50 ms, 256-bit 4.32 ms,
-// 256-bit no-allocate 4.17 ms; coalescing the rows across lanes changed nothing: the LSU queue counts instructions)
-__device__ __forceinline__ void dh_ld256(const float* p, float (&v)[8]) {
-    asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
-
 struct DhSlots {
     const float* wall;      // [18][2][8][64][4]: 9 blocks of 64 output rows x 2 K-halves, (hi, lo) canonical tiles
     unsigned char *s_B, *s_O, *s_KV;
@@ -442,7 +433,7 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
                     float t8[8];
-                    dh_ld256(src + i * 4, t8);
+                    etch_ld256_na(src + i * 4, t8);   // every 32-byte sector of the coarse features is read exactly once per tile (A/B: 128-bit __ldg 4.50 ms, 256-bit 4.32 ms, 256-bit no-allocate 4.17 ms; coalescing the rows across lanes changed nothing: the LSU queue counts instructions)
                     bv[k][i] = make_float4(t8[0], t8[1], t8[2], t8[3]);
                     bv[k][i + 1] = make_float4(t8[4], t8[5], t8[6], t8[7]);
                 }
