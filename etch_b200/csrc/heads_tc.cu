@@ -430,10 +430,13 @@ __global__ void __launch_bounds__(256, 1) direction_head_tc_kernel(
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const float* src = F + ((size_t)nb_idx[k] * DH_NA + ba) * 64 + bhf * 32;
+                // every 32-byte sector of the coarse features is read exactly once per tile: 256-bit loads that do not allocate in L1
+                // (A/B: 128-bit __ldg 4.50 ms, 256-bit 4.32 ms, 256-bit no-allocate 4.17 ms; coalescing the rows across lanes changed
+                // nothing: the LSU queue counts instructions)
 #pragma unroll
                 for (int i = 0; i < 8; i += 2) {
                     float t8[8];
-                    etch_ld256_na(src + i * 4, t8);   // every 32-byte sector of the coarse features is read exactly once per tile (A/B: 128-bit __ldg 4.50 ms, 256-bit 4.32 ms, 256-bit no-allocate 4.17 ms; coalescing the rows across lanes changed nothing: the LSU queue counts instructions)
+                    etch_ld256_na(src + i * 4, t8);
                     bv[k][i] = make_float4(t8[0], t8[1], t8[2], t8[3]);
                     bv[k][i + 1] = make_float4(t8[4], t8[5], t8[6], t8[7]);
                 }
