@@ -4,8 +4,11 @@
                                                             (the reference spends ~35 ms per file in a Python loop; this is one C call)
   results_to_host(fit)                                      ONE pinned device->host copy per batch of everything eval.py stores per scan
                                                             (the reference issues ~20 .detach().cpu().numpy() calls per scan)
+  save_tightness_vectors_info / save_output_smpl_info        the two .npz files eval.py writes per scan (same file names, keys, slices)
+  v2v_score / append_v2v_score / append_v2v_summary          the V2V number of eval.py and the lines of v2v_score.txt
 The colour PLYs and OBJ exports of eval.py go through trimesh / matplotlib (un-vendored third-party code) and stay the caller's."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -61,3 +64,50 @@ def results_to_host(fit, stream=None):
         out[k] = v.astype(np.int64) if k == "labels" else (v.astype(bool) if k == "valid" else v.copy())
         o += w
     return out
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def save_tightness_vectors_info(output_folder, id_, hitpts, pred_vectors, pred_part_labels, pred_confidences, gt_vectors, gt_labels,
+                                gt_confidences):
+    """src/eval.py:136-145: <output_folder>/<id>/tightness_vectors_info_<id>.npz with the reference's seven keys (one scan)."""
+    os.makedirs(os.path.join(output_folder, f"{id_}"), exist_ok=True)
+    path = os.path.join(output_folder, f"{id_}", f"tightness_vectors_info_{id_}.npz")
+    np.savez(path, hitpts=_np(hitpts), pred_vectors=_np(pred_vectors), pred_part_labels=_np(pred_part_labels),
+             pred_confidences=_np(pred_confidences), gt_vectors=_np(gt_vectors), gt_labels=_np(gt_labels),
+             gt_confidences=_np(gt_confidences))
+    return path
+
+
+def save_output_smpl_info(output_folder, id_, output_smpl_info, j):
+    """src/eval.py:239-246: <output_folder>/<id>/output_smpl_info_<id>.npz from fit_smpl's 5-list, sample j (21 body + 2 hand joints)."""
+    os.makedirs(os.path.join(output_folder, f"{id_}"), exist_ok=True)
+    path = os.path.join(output_folder, f"{id_}", f"output_smpl_info_{id_}.npz")
+    np.savez(path, body_pose=output_smpl_info[0][j][:21, :], hand_pose=output_smpl_info[0][j][21:23, :], betas=output_smpl_info[1][j],
+             global_orient=output_smpl_info[2][j], transl=output_smpl_info[3][j], joints=output_smpl_info[4][j])
+    return path
+
+
+def v2v_score(gt_vertices, pred_vertices):
+    """src/eval.py:233-236: mean Euclidean vertex distance, in float64 like the trimesh vertex arrays the reference subtracts."""
+    g, q = np.asarray(_np(gt_vertices), np.float64), np.asarray(_np(pred_vertices), np.float64)
+    return np.mean(np.linalg.norm(g - q, axis=1))
+
+
+def append_v2v_score(output_folder, id_, v2v, valid_mask_row):
+    """src/eval.py:251-252: one line of <output_folder>/v2v_score.txt, flagged when a marker of the scan was invalid."""
+    m = _np(valid_mask_row)
+    note = "  attention, the valid mask is not full" if int(m.sum()) != int(m.shape[0]) else ""
+    with open(os.path.join(output_folder, "v2v_score.txt"), "a") as f:
+        f.write(f"{id_}: {v2v}{note}\n")
+
+
+def append_v2v_summary(output_folder, total_v2v, sample_num):
+    """src/eval.py:258-262: the closing block of v2v_score.txt."""
+    with open(os.path.join(output_folder, "v2v_score.txt"), "a") as f:
+        f.write("==========\n")
+        f.write(f"average v2v: {total_v2v / sample_num}\n")
+        f.write(f"total v2v: {total_v2v}\n")
+        f.write(f"sample num: {sample_num}\n")
