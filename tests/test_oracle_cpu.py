@@ -175,6 +175,33 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert lib.etch_opt_threads(5000) == 1024 and lib.etch_opt_threads(600) == 512
 
 
+def test_hot_kernels_are_blackwell_native_sass():
+    """cuobjdump -sass of the built objects: the mnemonics B200_PROFILING.md names as proof of tcgen05 / TMEM / TMA code paths
+    (UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / .st, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk, SYNCS = mbarrier) and the
+    packed fma.rn.f32x2 (FFMA2) of the round-2 kernels.  No GPU needed."""
+    import shutil
+    import subprocess
+    from etch_b200 import build
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    build.build()
+
+    def mnemonics(name):
+        obj = os.path.join(ROOT, "etch_b200", "build", name + ".o")
+        sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+        assert "sm_100a" in sass
+        return set(re.findall(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", sass, re.M))
+
+    v3 = mnemonics("so3conv_v3")
+    assert {"UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "FFMA2"} <= v3, sorted(v3)
+    heads = mnemonics("heads_tc")
+    assert {"UTCHMMA", "LDTM", "UBLKCP", "SYNCS", "FFMA2"} <= heads
+    for name in ("so3conv_tc", "pt_tc", "linear_tc"):
+        assert {"UTCHMMA", "LDTM", "UBLKCP"} <= mnemonics(name), name
+    assert "UCGABAR_ARV" in mnemonics("index") or any(m.startswith("UCGABAR") for m in mnemonics("index"))   # cluster FPS
+
+
 def test_product_fails_loudly_without_cuda():
     """no CPU fallback: a CPU tensor is rejected instead of silently computed elsewhere."""
     from etch_b200.models.models_pointcloud import GT_network_equiv
